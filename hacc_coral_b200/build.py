@@ -1,0 +1,46 @@
+"""Build libhaccsr.so (and the C++ facade library) in-tree with nvcc for sm_100a."""
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+HOST = os.path.join(_HERE, "host")
+SOURCES = ["api.cu", "tree_build.cu", "walk.cu", "force.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _nvcc():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found; libhaccsr.so cannot be built")
+    return nvcc
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu -> csrc/libhaccsr.so and host/RCBForceTree.cxx -> host/libhaccsr_facade.so."""
+    out = os.path.join(CSRC, "libhaccsr.so")
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
+                                                       os.path.join(_HERE, "..", "include", "haccsr.h")]
+    if force or _stale(out, deps):
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        subprocess.check_call(cmd)
+    facade_src = os.path.join(HOST, "RCBForceTree.cxx")
+    if os.path.exists(facade_src):
+        fout = os.path.join(HOST, "libhaccsr_facade.so")
+        fdeps = [facade_src, os.path.join(HOST, "RCBForceTree.h"), os.path.join(HOST, "ForceLaw.h"), out]
+        if force or _stale(fout, [d for d in fdeps if os.path.exists(d)]):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", HOST,
+                                   "-I", os.path.join(_HERE, "..", "include"), "-o", fout, facade_src,
+                                   "-L", CSRC, "-lhaccsr", "-Wl,-rpath,$ORIGIN/../csrc"])
+    return out

@@ -1,0 +1,199 @@
+"""ctypes binding of libhaccsr.so (include/haccsr.h).  No CPU fallback: a missing library or a missing
+B200 raises HaccSRError."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+LAW_SR_POLY, LAW_NEWTON = 0, 3
+# reference src/halo_finder/ForceLaw.cxx:109-114 (== BGQStep16.c:167) and :98-104
+POLY5 = np.array([0.269327, -0.0750978, 0.0114808, -0.00109313, 0.0000605491, -0.00000147177], dtype=np.float32)
+POLY6 = np.array([0.271431, -0.0783394, 0.0133122, -0.00159485, 0.000132336, -0.00000663394, 0.000000147305],
+                 dtype=np.float32)
+RMAX = float(np.float32(3.116326355))   # reference ForceLaw.cxx:32
+
+
+class HaccSRError(RuntimeError):
+    pass
+
+
+class KickStats(C.Structure):
+    _fields_ = [("particles", C.c_int64), ("nodes", C.c_int64), ("leaves", C.c_int64),
+                ("empty_leaves", C.c_int64), ("max_ppn", C.c_int64), ("mean_ppn", C.c_double),
+                ("levels", C.c_int64), ("sink_leaves", C.c_int64), ("list_ranges", C.c_int64),
+                ("pseudo_particles", C.c_int64), ("max_list", C.c_int64), ("pairs_evaluated", C.c_uint64),
+                ("pairs_in_cutoff", C.c_uint64), ("ms_build", C.c_float), ("ms_walk", C.c_float),
+                ("ms_force", C.c_float), ("ms_total", C.c_float), ("force_launches", C.c_int32),
+                ("total_launches", C.c_int32)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class KickOpts(C.Structure):
+    _fields_ = [("count_in_cutoff", C.c_int32), ("skip_force", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "csrc", "libhaccsr.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """Load libhaccsr.so and declare every entry point of include/haccsr.h."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise HaccSRError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                          "there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    fp, ip64, u16p = C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_uint16)
+    vp = C.c_void_p
+    lib.haccsr_last_error.restype = C.c_char_p
+    lib.haccsr_device_count.restype = C.c_int
+    lib.haccsr_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int64]
+    lib.haccsr_destroy.argtypes = [vp]
+    lib.haccsr_set_stream.argtypes = [vp, vp]
+    lib.haccsr_set_force_law.argtypes = [vp, C.c_int, fp, C.c_int, C.c_float, C.c_float]
+    lib.haccsr_upload.argtypes = [vp, C.c_int64] + [fp] * 8 + [ip64, u16p]
+    lib.haccsr_download.argtypes = [vp, C.c_int64] + [fp] * 8 + [ip64, u16p]
+    lib.haccsr_host_register.argtypes = [vp, C.c_size_t]
+    lib.haccsr_host_unregister.argtypes = [vp]
+    lib.haccsr_kick.argtypes = [vp, C.c_int64, fp, fp, fp, fp, C.c_float, C.c_int64, C.c_int, C.c_float,
+                                C.POINTER(KickOpts), C.POINTER(KickStats)]
+    lib.haccsr_stream.argtypes = [vp, C.c_float]
+    lib.haccsr_partition_in_box.argtypes = [vp, fp, ip64]
+    lib.haccsr_fill_mass.argtypes = [vp, C.c_float]
+    i32p = C.POINTER(C.c_int32)
+    lib.haccsr_get_tree.argtypes = [vp, C.c_int64, ip64, i32p, i32p, i32p, i32p, fp]
+    u32p = C.POINTER(C.c_uint32)
+    lib.haccsr_get_lists.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, ip64, ip64, ip64, u32p, u32p, fp]
+    _LIB = lib
+    return lib
+
+
+EXPORTS = ["haccsr_last_error", "haccsr_device_count", "haccsr_create", "haccsr_destroy", "haccsr_set_stream",
+           "haccsr_set_force_law", "haccsr_upload", "haccsr_download", "haccsr_host_register",
+           "haccsr_host_unregister", "haccsr_kick", "haccsr_stream", "haccsr_partition_in_box",
+           "haccsr_fill_mass", "haccsr_get_tree", "haccsr_get_lists"]
+
+_F32 = ("x", "y", "z", "vx", "vy", "vz", "mass", "phi")
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(t) for t in v])
+
+
+class HaccSR:
+    """One context on one GPU: upload -> [stream, kick, stream]* -> download."""
+
+    def __init__(self, max_particles, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        self._h = None
+        self._check(self.lib.haccsr_create(C.byref(h), device, int(max_particles)))
+        self._h = h
+        self.n = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HaccSRError("libhaccsr: %s (status %d)" % (self.lib.haccsr_last_error().decode(), rc))
+
+    def close(self):
+        if self._h is not None:
+            self.lib.haccsr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.haccsr_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_force_law(self, kind=LAW_SR_POLY, coeffs=POLY5, rsm=0.007, rmax=RMAX):
+        coeffs = np.ascontiguousarray(coeffs if coeffs is not None else [], dtype=np.float32)
+        self._check(self.lib.haccsr_set_force_law(self._h, kind, _fp(coeffs), int(coeffs.size), rsm, rmax))
+
+    def upload(self, p):
+        n = int(np.asarray(p["x"]).size)
+        a = {k: np.ascontiguousarray(p[k], dtype=np.float32) for k in _F32 if k in p}
+        ids = np.ascontiguousarray(p["id"], dtype=np.int64) if "id" in p else None
+        mask = np.ascontiguousarray(p["mask"], dtype=np.uint16) if "mask" in p else None
+        self._check(self.lib.haccsr_upload(
+            self._h, n, *[_fp(a.get(k)) for k in _F32],
+            ids.ctypes.data_as(C.POINTER(C.c_int64)) if ids is not None else None,
+            mask.ctypes.data_as(C.POINTER(C.c_uint16)) if mask is not None else None))
+        self.n = n
+
+    def download(self, n=None, out=None):
+        n = self.n if n is None else n
+        if out is None:
+            out = {k: np.empty(n, dtype=np.float32) for k in _F32}
+            out["id"] = np.empty(n, dtype=np.int64)
+            out["mask"] = np.empty(n, dtype=np.uint16)
+        self._check(self.lib.haccsr_download(
+            self._h, n, *[_fp(out.get(k)) for k in _F32],
+            out["id"].ctypes.data_as(C.POINTER(C.c_int64)) if out.get("id") is not None else None,
+            out["mask"].ctypes.data_as(C.POINTER(C.c_uint16)) if out.get("mask") is not None else None))
+        return out
+
+    def kick(self, tree_lo, tree_hi, force_lo, force_hi, theta, ppn, fcoeff=1.0, count=None,
+             count_in_cutoff=False, skip_force=False, tdpts=1):
+        st = KickStats()
+        opts = KickOpts()
+        opts.count_in_cutoff = int(count_in_cutoff)
+        opts.skip_force = int(skip_force)
+        n = self.n if count is None else count
+        self._check(self.lib.haccsr_kick(self._h, n, _f3(tree_lo), _f3(tree_hi), _f3(force_lo), _f3(force_hi),
+                                         theta, int(ppn), tdpts, fcoeff, C.byref(opts), C.byref(st)))
+        return st.as_dict()
+
+    def stream(self, prefactor_tau):
+        self._check(self.lib.haccsr_stream(self._h, prefactor_tau))
+
+    def fill_mass(self, value=1.0):
+        self._check(self.lib.haccsr_fill_mass(self._h, value))
+
+    def partition_in_box(self, hi):
+        nin = C.c_int64()
+        self._check(self.lib.haccsr_partition_in_box(self._h, _f3(hi), C.byref(nin)))
+        return nin.value
+
+    def tree(self):
+        nn = C.c_int64()
+        self._check(self.lib.haccsr_get_tree(self._h, 0, C.byref(nn), None, None, None, None, None))
+        m = nn.value
+        t = {k: np.empty(m, dtype=np.int32) for k in ("count", "offset", "cl", "cr")}
+        box = np.empty((m, 10), dtype=np.float32)
+        i32p = C.POINTER(C.c_int32)
+        self._check(self.lib.haccsr_get_tree(self._h, m, C.byref(nn), t["count"].ctypes.data_as(i32p),
+                                             t["offset"].ctypes.data_as(i32p), t["cl"].ctypes.data_as(i32p),
+                                             t["cr"].ctypes.data_as(i32p), _fp(box)))
+        t["xmin"], t["xmax"], t["xc"], t["ppm"] = box[:, 0:3], box[:, 3:6], box[:, 6:9], box[:, 9]
+        return t
+
+    def lists(self):
+        nn, nr, npool = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.haccsr_get_lists(self._h, 0, 0, 0, C.byref(nn), C.byref(nr), C.byref(npool),
+                                              None, None, None))
+        off = np.empty(nn.value + 1, dtype=np.uint32)
+        ranges = np.empty((max(nr.value, 1), 2), dtype=np.uint32)
+        pool = np.empty((max(npool.value, 1), 4), dtype=np.float32)
+        u32p = C.POINTER(C.c_uint32)
+        self._check(self.lib.haccsr_get_lists(self._h, nn.value + 1, max(nr.value, 1), max(npool.value, 1),
+                                              C.byref(nn), C.byref(nr), C.byref(npool), off.ctypes.data_as(u32p),
+                                              ranges.ctypes.data_as(u32p), _fp(pool)))
+        return {"range_off": off, "ranges": ranges[:nr.value], "pool": pool[:npool.value]}

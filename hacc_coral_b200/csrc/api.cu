@@ -1,0 +1,356 @@
+// api.cu -- the C ABI of libhaccsr.so (include/haccsr.h): context, transfers, the kick orchestration and
+// the small HBM-bound helpers around it (stream = Particles::map1, out-of-box compaction, mass fill).
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+namespace haccsr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int alloc_soa(Soa &s, int64_t n) {
+  size_t m = (size_t)n + 64;
+  float **f[8] = {&s.x, &s.y, &s.z, &s.vx, &s.vy, &s.vz, &s.mass, &s.phi};
+  for (int i = 0; i < 8; ++i) HSR_CUDA(cudaMalloc((void **)f[i], m * sizeof(float)));
+  HSR_CUDA(cudaMalloc((void **)&s.id, m * sizeof(int64_t)));
+  HSR_CUDA(cudaMalloc((void **)&s.mask, m * sizeof(uint16_t)));
+  return 0;
+}
+static void free_soa(Soa &s) {
+  float *f[8] = {s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, s.phi};
+  for (int i = 0; i < 8; ++i) if (f[i]) cudaFree(f[i]);
+  if (s.id) cudaFree(s.id);
+  if (s.mask) cudaFree(s.mask);
+  memset(&s, 0, sizeof(s));
+}
+
+// x += pt * v   (Particles::map1, reference src/cpu/Particles.cxx:745-755; pt = prefactor * tau).
+// The reference evaluates x + (prefactor*tau)*v with a float multiply then a float add; kept unfused.
+__global__ void __launch_bounds__(256) k_stream(float *__restrict__ x, float *__restrict__ y, float *__restrict__ z,
+                                                const float *__restrict__ vx, const float *__restrict__ vy,
+                                                const float *__restrict__ vz, float pt, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    x[i] = __fadd_rn(x[i], __fmul_rn(pt, vx[i]));
+    y[i] = __fadd_rn(y[i], __fmul_rn(pt, vy[i]));
+    z[i] = __fadd_rn(z[i], __fmul_rn(pt, vz[i]));
+  }
+}
+
+__global__ void __launch_bounds__(256) k_fill(float *__restrict__ a, float v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] = v;
+}
+
+// in-box flag per particle: 0 <= floor(x) < hi in every dimension (Particles::resortParticles uses
+// array_index on floor'ed coordinates; anything outside the local grid lands in the overflow cell Ng,
+// reference src/cpu/Particles.cxx:434-443).
+__global__ void __launch_bounds__(256) k_inbox_flags(const float *__restrict__ x, const float *__restrict__ y,
+                                                     const float *__restrict__ z, float3 hi, long long n,
+                                                     unsigned *__restrict__ flag) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float fx = floorf(x[i]), fy = floorf(y[i]), fz = floorf(z[i]);
+    bool in = fx >= 0.f && fx < hi.x && fy >= 0.f && fy < hi.y && fz >= 0.f && fz < hi.z;
+    flag[i] = in ? 1u : 0u;
+  }
+}
+__global__ void __launch_bounds__(256) k_compact(Soa in, Soa out, const unsigned *__restrict__ flag,
+                                                 const unsigned *__restrict__ pref, unsigned n_in, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned p = pref[i];
+    long long d = flag[i] ? (long long)p : (long long)n_in + (i - (long long)p);
+    out.x[d] = in.x[i]; out.y[d] = in.y[i]; out.z[d] = in.z[i];
+    out.vx[d] = in.vx[i]; out.vy[d] = in.vy[i]; out.vz[d] = in.vz[i];
+    out.mass[d] = in.mass[i]; out.phi[d] = in.phi[i]; out.id[d] = in.id[i]; out.mask[d] = in.mask[i];
+  }
+}
+
+static int lin_grid(const haccsr_ctx *c, int64_t n) {
+  int64_t g = (n + 255) / 256;
+  int64_t cap = (int64_t)c->sm_count * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace haccsr
+
+using namespace haccsr;
+
+extern "C" {
+
+const char *haccsr_last_error(void) { return g_err; }
+
+int haccsr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ok++;
+  }
+  return ok;
+}
+
+int haccsr_create(haccsr_ctx **out, int device, int64_t max_particles) {
+  if (!out) { set_error("haccsr_create: out is NULL"); return 1; }
+  *out = nullptr;
+  if (max_particles < 0 || max_particles > 2000000000ll) { set_error("haccsr_create: bad max_particles"); return 1; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available (%s); libhaccsr has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return 3;
+  }
+  if (device < 0 || device >= ndev) { set_error("haccsr_create: device %d out of range (have %d)", device, ndev); return 1; }
+  cudaDeviceProp prop;
+  HSR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libhaccsr is built for sm_100a only", device, prop.major, prop.minor);
+    return 3;
+  }
+  HSR_CUDA(cudaSetDevice(device));
+  haccsr_ctx *c = new (std::nothrow) haccsr_ctx();
+  if (!c) { set_error("out of host memory"); return 2; }
+  c->device = device; c->sm_count = prop.multiProcessorCount; c->cap = max_particles;
+  int rc = 0;
+  do {
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = 2; break; }
+    c->stream = c->own_stream;
+    if ((rc = alloc_soa(c->cur, max_particles))) break;
+    if ((rc = alloc_soa(c->alt, max_particles))) break;
+    if (cudaMallocHost((void **)&c->h_level, sizeof(LevelInfo)) != cudaSuccess) { rc = 2; break; }
+    if (cudaMalloc((void **)&c->d_level, sizeof(LevelInfo)) != cudaSuccess) { rc = 2; break; }
+    if (cudaMallocHost((void **)&c->h_counters, 16 * sizeof(int64_t)) != cudaSuccess) { rc = 2; break; }
+    if (cudaMalloc((void **)&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) { rc = 2; break; }
+    for (int i = 0; i < 5; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { rc = 2; break; }
+  } while (0);
+  if (rc) {
+    if (g_err[0] == 0 || rc == 2) set_error("haccsr_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    haccsr_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+int haccsr_destroy(haccsr_ctx *c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_soa(c->cur); free_soa(c->alt);
+  c->recA.release(); c->recB.release(); c->src4.release(); c->idxA.release(); c->idxB.release(); c->perm.release();
+  c->nidA.release(); c->nidB.release(); c->nodes.release(); c->acc.release(); c->lstart.release(); c->lend.release();
+  c->lbase.release(); c->nleft.release(); c->tilecount.release(); c->tilebase.release(); c->scratch_u32.release();
+  c->n_ranges.release(); c->n_pseudo.release(); c->range_off.release(); c->pseudo_off.release(); c->list_len.release();
+  c->ranges.release(); c->pool.release(); c->item_cnt.release(); c->item_off.release(); c->items.release();
+  if (c->h_level) cudaFreeHost(c->h_level);
+  if (c->d_level) cudaFree(c->d_level);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->d_counters) cudaFree(c->d_counters);
+  for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return 0;
+}
+
+int haccsr_set_stream(haccsr_ctx *c, void *cuda_stream) {
+  if (!c) { set_error("null context"); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  HSR_CUDA(cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return 0;
+}
+
+int haccsr_set_force_law(haccsr_ctx *c, int kind, const float *coeffs, int ncoef, float rsm, float rmax) {
+  if (!c) { set_error("null context"); return 1; }
+  if (kind != HACCSR_LAW_SR_POLY && kind != HACCSR_LAW_NEWTON) {
+    set_error("unsupported force law kind %d (supported: SR_POLY=0, NEWTON=3); no CPU fallback", kind);
+    return 1;
+  }
+  if (kind == HACCSR_LAW_SR_POLY && (ncoef < 1 || ncoef > 7 || !coeffs)) { set_error("SR_POLY needs 1..7 coefficients"); return 1; }
+  if (!(rmax > 0.f)) { set_error("rmax must be positive"); return 1; }
+  memset(&c->law, 0, sizeof(c->law));
+  c->law.kind = kind;
+  c->law.ncoef = (kind == HACCSR_LAW_SR_POLY) ? ncoef : 0;
+  for (int i = 0; i < c->law.ncoef; ++i) c->law.a[i] = coeffs[i];
+  c->law.rsm2 = (kind == HACCSR_LAW_NEWTON) ? 0.0f : rsm * rsm;   // ForceLaw.cxx:177 (m_rsm2 = rsm*rsm, float)
+  c->law.rmax = rmax;
+  c->law.rmax2 = rmax * rmax;                                     // RCBForceTree.cxx:582 (float product)
+  c->law_set = true;
+  return 0;
+}
+
+#define COPY_H2D(dst, src, bytes) do { if (src) HSR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream)); } while (0)
+#define COPY_D2H(dst, src, bytes) do { if (dst) HSR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream)); } while (0)
+
+int haccsr_upload(haccsr_ctx *c, int64_t n, const float *x, const float *y, const float *z, const float *vx,
+                  const float *vy, const float *vz, const float *mass, const float *phi, const int64_t *id,
+                  const uint16_t *mask) {
+  if (!c) { set_error("null context"); return 1; }
+  if (n < 0 || n > c->cap) { set_error("haccsr_upload: count %lld exceeds capacity %lld", (long long)n, (long long)c->cap); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  size_t fb = (size_t)n * sizeof(float);
+  if (!x || !y || !z || !vx || !vy || !vz || !mass) { set_error("haccsr_upload: x y z vx vy vz mass are required"); return 1; }
+  COPY_H2D(c->cur.x, x, fb); COPY_H2D(c->cur.y, y, fb); COPY_H2D(c->cur.z, z, fb);
+  COPY_H2D(c->cur.vx, vx, fb); COPY_H2D(c->cur.vy, vy, fb); COPY_H2D(c->cur.vz, vz, fb);
+  COPY_H2D(c->cur.mass, mass, fb);
+  if (phi) { COPY_H2D(c->cur.phi, phi, fb); } else { HSR_CUDA(cudaMemsetAsync(c->cur.phi, 0, fb, c->stream)); }
+  if (id) { COPY_H2D(c->cur.id, id, (size_t)n * sizeof(int64_t)); } else { HSR_CUDA(cudaMemsetAsync(c->cur.id, 0, (size_t)n * sizeof(int64_t), c->stream)); }
+  if (mask) { COPY_H2D(c->cur.mask, mask, (size_t)n * sizeof(uint16_t)); } else { HSR_CUDA(cudaMemsetAsync(c->cur.mask, 0, (size_t)n * sizeof(uint16_t), c->stream)); }
+  HSR_CUDA(cudaStreamSynchronize(c->stream));
+  c->n_resident = n;
+  return 0;
+}
+
+int haccsr_download(haccsr_ctx *c, int64_t n, float *x, float *y, float *z, float *vx, float *vy, float *vz,
+                    float *mass, float *phi, int64_t *id, uint16_t *mask) {
+  if (!c) { set_error("null context"); return 1; }
+  if (n < 0 || n > c->n_resident) { set_error("haccsr_download: count %lld exceeds resident %lld", (long long)n, (long long)c->n_resident); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  size_t fb = (size_t)n * sizeof(float);
+  COPY_D2H(x, c->cur.x, fb); COPY_D2H(y, c->cur.y, fb); COPY_D2H(z, c->cur.z, fb);
+  COPY_D2H(vx, c->cur.vx, fb); COPY_D2H(vy, c->cur.vy, fb); COPY_D2H(vz, c->cur.vz, fb);
+  COPY_D2H(mass, c->cur.mass, fb); COPY_D2H(phi, c->cur.phi, fb);
+  COPY_D2H(id, c->cur.id, (size_t)n * sizeof(int64_t)); COPY_D2H(mask, c->cur.mask, (size_t)n * sizeof(uint16_t));
+  HSR_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int haccsr_host_register(void *ptr, size_t bytes) {
+  if (!ptr || !bytes) return 0;
+  HSR_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return 0;
+}
+int haccsr_host_unregister(void *ptr) {
+  if (!ptr) return 0;
+  HSR_CUDA(cudaHostUnregister(ptr));
+  return 0;
+}
+
+int haccsr_kick(haccsr_ctx *c, int64_t count, const float tree_lo[3], const float tree_hi[3], const float force_lo[3],
+                const float force_hi[3], float theta, int64_t ppn, int tdpts, float fcoeff,
+                const haccsr_kick_opts *opts, haccsr_stats *stats) {
+  if (!c) { set_error("null context"); return 1; }
+  if (!c->law_set) { set_error("haccsr_kick: force law not set"); return 1; }
+  if (tdpts != 1) { set_error("haccsr_kick: only the monopole tree (TDPTS = 1, -R) is implemented; got %d", tdpts); return 1; }
+  if (count < 0 || count > c->n_resident) { set_error("haccsr_kick: count %lld exceeds resident %lld", (long long)count, (long long)c->n_resident); return 1; }
+  if (ppn < 1) { set_error("haccsr_kick: ppn must be >= 1"); return 1; }
+  if (!tree_lo || !tree_hi || !force_lo || !force_hi) { set_error("haccsr_kick: null box"); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  haccsr_stats local; memset(&local, 0, sizeof(local));
+  haccsr_stats *st = stats ? stats : &local;
+  memset(st, 0, sizeof(*st));
+  st->particles = count;
+  const bool count_cut = opts && opts->count_in_cutoff;
+  const bool skip_force = opts && opts->skip_force;
+  c->launches = 0; c->force_launches = 0;
+  cudaStream_t s = c->stream;
+  HSR_CUDA(cudaEventRecord(c->ev[0], s));
+  HSR_TRY(build_tree(c, count, tree_lo, tree_hi, ppn));
+  HSR_CUDA(cudaEventRecord(c->ev[1], s));
+  HSR_TRY(build_lists(c, force_lo, force_hi, theta, st));
+  HSR_CUDA(cudaEventRecord(c->ev[2], s));
+  if (!skip_force) HSR_TRY(run_force(c, fcoeff, count_cut, st));
+  HSR_CUDA(cudaEventRecord(c->ev[3], s));
+  HSR_CUDA(cudaStreamSynchronize(s));
+  HSR_CUDA(cudaGetLastError());
+  HSR_CUDA(cudaEventElapsedTime(&st->ms_build, c->ev[0], c->ev[1]));
+  HSR_CUDA(cudaEventElapsedTime(&st->ms_walk, c->ev[1], c->ev[2]));
+  HSR_CUDA(cudaEventElapsedTime(&st->ms_force, c->ev[2], c->ev[3]));
+  HSR_CUDA(cudaEventElapsedTime(&st->ms_total, c->ev[0], c->ev[3]));
+  st->force_launches = c->force_launches; st->total_launches = c->launches;
+  return 0;
+}
+
+int haccsr_stream(haccsr_ctx *c, float pt) {
+  if (!c) { set_error("null context"); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  if (c->n_resident == 0) return 0;
+  k_stream<<<lin_grid(c, c->n_resident), 256, 0, c->stream>>>(c->cur.x, c->cur.y, c->cur.z, c->cur.vx, c->cur.vy,
+                                                              c->cur.vz, pt, (long long)c->n_resident);
+  HSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int haccsr_fill_mass(haccsr_ctx *c, float value) {
+  if (!c) { set_error("null context"); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  if (c->n_resident == 0) return 0;
+  k_fill<<<lin_grid(c, c->n_resident), 256, 0, c->stream>>>(c->cur.mass, value, (long long)c->n_resident);
+  HSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int haccsr_partition_in_box(haccsr_ctx *c, const float hi[3], int64_t *count_in_box) {
+  if (!c) { set_error("null context"); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  const int64_t n = c->n_resident;
+  if (n == 0) { if (count_in_box) *count_in_box = 0; return 0; }
+  // flags / prefixes borrow the build's index buffers (they are rebuilt by every kick)
+  HSR_TRY(c->idxA.ensure((size_t)n + 1)); HSR_TRY(c->idxB.ensure((size_t)n + 1));
+  const int g = lin_grid(c, n);
+  k_inbox_flags<<<g, 256, 0, c->stream>>>(c->cur.x, c->cur.y, c->cur.z, make_float3(hi[0], hi[1], hi[2]), (long long)n, c->idxA.p);
+  HSR_TRY(scan_exclusive(c, c->idxA.p, c->idxB.p, n, c->d_counters + 12));
+  HSR_CUDA(cudaMemcpyAsync(c->h_counters + 12, c->d_counters + 12, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  HSR_CUDA(cudaStreamSynchronize(c->stream));
+  const int64_t nin = c->h_counters[12];
+  k_compact<<<g, 256, 0, c->stream>>>(c->cur, c->alt, c->idxA.p, c->idxB.p, (unsigned)nin, (long long)n);
+  HSR_CUDA(cudaGetLastError());
+  Soa t = c->cur; c->cur = c->alt; c->alt = t;
+  if (count_in_box) *count_in_box = nin;
+  return 0;
+}
+
+int haccsr_get_tree(haccsr_ctx *c, int64_t cap, int64_t *nodes, int32_t *count, int32_t *offset, int32_t *cl,
+                    int32_t *cr, float *box10) {
+  if (!c) { set_error("null context"); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  if (nodes) *nodes = c->n_nodes;
+  if (cap == 0) return 0;
+  if (cap < c->n_nodes) { set_error("haccsr_get_tree: cap %lld < nodes %d", (long long)cap, c->n_nodes); return 1; }
+  Node *h = (Node *)malloc((size_t)c->n_nodes * sizeof(Node));
+  if (!h) { set_error("out of host memory"); return 2; }
+  cudaError_t e = cudaMemcpy(h, c->nodes.p, (size_t)c->n_nodes * sizeof(Node), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { free(h); set_error("cudaMemcpy nodes: %s", cudaGetErrorString(e)); return 2; }
+  for (int i = 0; i < c->n_nodes; ++i) {
+    if (count) count[i] = h[i].count;
+    if (offset) offset[i] = h[i].offset;
+    if (cl) cl[i] = h[i].cl;
+    if (cr) cr[i] = h[i].cr;
+    if (box10) {
+      for (int k = 0; k < 3; ++k) { box10[10*i + k] = h[i].xmin[k]; box10[10*i + 3 + k] = h[i].xmax[k]; box10[10*i + 6 + k] = h[i].xc[k]; }
+      box10[10*i + 9] = h[i].ppm;
+    }
+  }
+  free(h);
+  return 0;
+}
+
+int haccsr_get_lists(haccsr_ctx *c, int64_t cap_nodes, int64_t cap_ranges, int64_t cap_pool, int64_t *n_nodes,
+                     int64_t *n_ranges, int64_t *n_pool, uint32_t *range_off, uint32_t *ranges, float *pool) {
+  if (!c) { set_error("null context"); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  if (n_nodes) *n_nodes = c->n_nodes;
+  if (n_ranges) *n_ranges = c->tot_ranges;
+  if (n_pool) *n_pool = c->tot_pseudo;
+  if (cap_nodes == 0 && cap_ranges == 0 && cap_pool == 0) return 0;
+  if (cap_nodes < c->n_nodes + 1 || cap_ranges < c->tot_ranges || cap_pool < c->tot_pseudo) { set_error("haccsr_get_lists: buffers too small"); return 1; }
+  HSR_CUDA(cudaStreamSynchronize(c->stream));
+  if (range_off) HSR_CUDA(cudaMemcpy(range_off, c->range_off.p, (size_t)(c->n_nodes + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  if (ranges && c->tot_ranges) HSR_CUDA(cudaMemcpy(ranges, c->ranges.p, (size_t)c->tot_ranges * sizeof(uint2), cudaMemcpyDeviceToHost));
+  if (pool && c->tot_pseudo) HSR_CUDA(cudaMemcpy(pool, c->pool.p, (size_t)c->tot_pseudo * sizeof(float4), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

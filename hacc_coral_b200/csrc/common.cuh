@@ -1,0 +1,151 @@
+// common.cuh -- shared declarations of libhaccsr (internal; the public ABI is include/haccsr.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/haccsr.h"
+
+namespace haccsr {
+
+// ---------------------------------------------------------------------------------------------
+// Error plumbing: every CUDA call is checked; failures become a status + thread-local message.
+void set_error(const char *fmt, ...);
+#define HSR_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      haccsr::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return 2;                                                                                \
+    }                                                                                          \
+  } while (0)
+#define HSR_TRY(call)                                                                          \
+  do {                                                                                         \
+    int rc__ = (call);                                                                         \
+    if (rc__ != 0) return rc__;                                                                \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Device data layout (all in HBM; sizes for N particles):
+//   Particle SoA `Soa`: the reference's 10 arrays (src/cpu/Particles.h:195-205), 42 B/particle, two sets
+//   (cur / alt) so the permutation into tree order is an out-of-place gather.
+//   src4: packed (x,y,z,mass) float4 in TREE ORDER -- the force kernel's source/sink array; any range
+//   of it is 16-B aligned so it can be moved by 1-D TMA bulk copies.
+struct Soa {
+  float *x, *y, *z, *vx, *vy, *vz, *mass, *phi;
+  int64_t *id;
+  uint16_t *mask;
+};
+
+// Tree node, 64 B, read by the walk as four 16-B loads.  Mirrors TreeNode
+// (reference src/halo_finder/RCBForceTree.h:131-147) for TDPTS = 1.
+struct __align__(16) Node {
+  int count, offset, cl, cr;     // particles in node, first particle (tree order), children (0 = none)
+  float xmin[3], xmax[3];        // tight bounding box
+  float xc[3];                   // centre of mass
+  float ppm;                     // monopole pseudo-particle mass
+  int parent;
+  int split;                     // build-time: split dimension 0..2, or -1 for a leaf
+};
+static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
+
+// Build-time accumulators of a node: order-independent (integer) so the build is deterministic.
+struct NodeAcc {
+  unsigned umin[3], umax[3];         // order-preserving uint encoding of float min / max
+  unsigned long long lo[4], hi[4];   // 128-bit fixed-point sums of w*x, w*y, w*z, w
+};
+
+struct ForceLawParams {
+  int kind;          // HACCSR_LAW_*
+  int ncoef;         // number of polynomial coefficients in use (<= 7)
+  float a[7];
+  float rsm2, rmax2, rmax;
+};
+
+// Range-list entry flag: start index refers to the pseudo-particle pool.
+static constexpr unsigned POOL_FLAG = 0x80000000u;
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;  // elements
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e));
+      return 2;
+    }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Per-level bookkeeping written by the device and read by the host after each level.
+struct LevelInfo {
+  int begin, end;     // node index range of the NEXT level
+  int nsplit;         // nodes split at this level
+  int error;          // 1 = node pool exhausted
+};
+
+struct WorkItem { int node, sink_begin, sink_count, pad; };
+
+}  // namespace haccsr
+
+struct haccsr_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int sm_count = 0;
+  int64_t cap = 0;       // particle capacity
+  int64_t n_resident = 0;
+  haccsr::Soa cur{}, alt{};
+  haccsr::ForceLawParams law{};
+  bool law_set = false;
+
+  // build scratch
+  haccsr::DevBuf<float4> recA, recB, src4;          // ping-pong (x,y,z,m) records, final tree-order array
+  haccsr::DevBuf<unsigned> idxA, idxB, perm;        // original index travelling with the record; final perm
+  haccsr::DevBuf<int> nidA, nidB;                   // node owning each position at the current level (-1 = final)
+  haccsr::DevBuf<haccsr::Node> nodes;
+  haccsr::DevBuf<haccsr::NodeAcc> acc;
+  haccsr::DevBuf<int> lstart, lend, lbase, nleft;   // per node: local prefixes at first / last particle, L(o_k), is_k
+  haccsr::DevBuf<unsigned> tilecount, tilebase;     // per tile: left count, exclusive scan
+  haccsr::DevBuf<unsigned> scratch_u32;             // maxima for the fixed-point scales etc.
+  haccsr::LevelInfo *h_level = nullptr;             // pinned
+  haccsr::LevelInfo *d_level = nullptr;
+  int64_t *h_counters = nullptr;                    // pinned, misc read-backs
+  unsigned long long *d_counters = nullptr;
+
+  // tree of the last kick
+  int64_t n_tree = 0;       // particles in the tree
+  int n_nodes = 0, n_levels = 0;
+  int level_begin[128], level_end[128];
+
+  // walk output
+  haccsr::DevBuf<unsigned> n_ranges, n_pseudo, range_off, pseudo_off, list_len;   // per node
+  haccsr::DevBuf<uint2> ranges;
+  haccsr::DevBuf<float4> pool;
+  int64_t tot_ranges = 0, tot_pseudo = 0;
+
+  // force work items
+  haccsr::DevBuf<unsigned> item_cnt, item_off;
+  haccsr::DevBuf<haccsr::WorkItem> items;
+  int64_t n_items = 0;
+
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int launches = 0, force_launches = 0;
+};
+
+namespace haccsr {
+// tree_build.cu
+int build_tree(haccsr_ctx *c, int64_t n, const float lo[3], const float hi[3], int64_t ppn);
+// walk.cu
+int build_lists(haccsr_ctx *c, const float flo[3], const float fhi[3], float theta, haccsr_stats *st);
+// force.cu
+int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *st);
+// scan utility (tree_build.cu): exclusive scan of n unsigned values; total written to *d_total (device).
+int scan_exclusive(haccsr_ctx *c, const unsigned *in, unsigned *out, int64_t n, unsigned long long *d_total);
+}  // namespace haccsr

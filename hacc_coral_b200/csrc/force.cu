@@ -1,0 +1,290 @@
+// force.cu -- the leaf-vs-list short-range force kernel and kick, sm_100a.
+//
+// Computes, for every particle i of every sink leaf, the sum over the leaf's interaction list
+//     a_i = sum_j m_j f(r2_ij) (x_j - x_i),   f(r2) = (r2 + rsm^2)^-3/2 - poly(r2)   for r2 < rmax^2, else 0
+// and kicks v_i += fcoeff * m_i * a_i.  This is nbody1 (reference src/halo_finder/RCBForceTree.cxx:575-620)
+// in the accumulate-then-scale form of the BG/Q kernel (src/halo_finder/BGQStep16.c:170-187 with
+// RCBForceTree.cxx:594-596); the force law is ForceLawSR over FGridEvalPoly (ForceLaw.cxx:137-141,187-192).
+//
+// Mapping to the B200 (FP32-FMA-pipe bound; no tensor cores -- this is not a contraction):
+//  * one WARP per work item = (sink leaf, chunk of <= 32*SMAX_ sinks); one warp per CTA, so the producer /
+//    consumer hand-off needs no block barrier, only mbarriers and __syncwarp.
+//  * each thread keeps S sinks (position + accumulator) in registers; S = ceil(chunk/32) is picked per item,
+//    so a 300-particle leaf runs at 94 % lane utilisation instead of 59 % with a fixed 512-slot block.
+//  * sources stream through a 4-stage shared-memory ring of 128-source float4 tiles.  Every list range is
+//    a contiguous, 16-B aligned piece of the tree-ordered float4 array (or of the pseudo-particle pool),
+//    so lane 0 moves it with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx::bytes);
+//    the warp then reads each source once with a broadcast LDS.128 and applies it to its S sinks.
+//  * r2 is formed with separate multiplies and adds in the reference's order (no FMA contraction), so the
+//    set of pairs inside the cutoff is bit-identical to the CPU's; everything after r2 uses FMAs.
+//  * (r2+rsm^2)^-3/2 = rsqrt((r2+rsm^2)^3) with MUFU.RSQ (rsqrt.approx.ftz), Horner polynomial in FMAs,
+//    cutoff as one compare + select on the per-pair scalar.
+// Reduction order (documented for the parity gate): each sink accumulates sequentially over its list in
+// list order, in FP32, in one thread -- no cross-lane reduction is needed because sinks, not sources, are
+// spread over lanes.
+#include "common.cuh"
+
+namespace haccsr {
+
+static constexpr int SMAX_ = 8;        // max sinks per thread
+static constexpr int FTILE = 128;      // sources per shared-memory tile
+static constexpr int FSTAGES = 4;      // ring depth
+
+struct ForceParams {
+  const WorkItem *items;
+  const unsigned *range_off;   // per node
+  const uint2 *ranges;
+  const unsigned *list_len;    // per node
+  const float4 *src4;
+  const float4 *pool;
+  float *vx, *vy, *vz;
+  unsigned long long *incut;   // optional counter
+  float a[7];
+  float rsm2, rmax2, fcoeff;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// One source applied to S sinks.  LAW: 0 = SR-poly with NC coefficients, 1 = Newton.
+template <int S, int NC, int LAW, bool GUARD0, bool COUNT>
+__device__ __forceinline__ void interact(const float4 s, const float (&xi)[S], const float (&yi)[S],
+                                         const float (&zi)[S], float (&ax)[S], float (&ay)[S], float (&az)[S],
+                                         const ForceParams &P, unsigned (&cnt)[S]) {
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    float dx = __fsub_rn(s.x, xi[k]), dy = __fsub_rn(s.y, yi[k]), dz = __fsub_rn(s.z, zi[k]);
+    // reference order, no contraction: (dx*dx + dy*dy) + dz*dz   (RCBForceTree.cxx:608, BGQStep16.c:176)
+    float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    float t = r2 + P.rsm2;
+    float f = rsqrt_ftz(t * t * t);
+    if (LAW == 0) {
+      float p = P.a[NC - 1];
+#pragma unroll
+      for (int q = NC - 2; q >= 0; --q) p = fmaf(p, r2, P.a[q]);
+      f -= p;
+    }
+    f *= s.w;
+    bool in = r2 < P.rmax2;
+    if (GUARD0) in = in && (r2 > 0.0f);
+    f = in ? f : 0.0f;
+    if (COUNT) cnt[k] += (in && r2 > 0.0f) ? 1u : 0u;
+    ax[k] = fmaf(f, dx, ax[k]); ay[k] = fmaf(f, dy, ay[k]); az[k] = fmaf(f, dz, az[k]);
+  }
+}
+
+struct Producer {
+  const uint2 *ranges;
+  unsigned ri, rend;      // current / end range index
+  unsigned roff;          // sources already taken from the current range
+  unsigned remaining;     // sources still to be fetched
+};
+
+// lane 0 only: post the copies of the next tile into `stage`
+__device__ __forceinline__ void produce_tile(Producer &pr, const ForceParams &P, float4 *tile, unsigned bar) {
+  unsigned n = pr.remaining < (unsigned)FTILE ? pr.remaining : (unsigned)FTILE;
+  if (n == 0) return;
+  mbar_expect_tx(bar, n * 16u);
+  unsigned pos = 0;
+  while (pos < n) {
+    uint2 r = __ldg(pr.ranges + pr.ri);
+    unsigned take = r.y - pr.roff;
+    if (take > n - pos) take = n - pos;
+    const float4 *base = (r.x & POOL_FLAG) ? (P.pool + (r.x & ~POOL_FLAG)) : (P.src4 + r.x);
+    bulk_g2s(smem_u32(tile + pos), base + pr.roff, take * 16u, bar);
+    pos += take; pr.roff += take;
+    if (pr.roff == r.y) { pr.ri++; pr.roff = 0; }
+  }
+  pr.remaining -= n;
+}
+
+template <int S, int NC, int LAW, bool GUARD0, bool COUNT>
+__device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P, float4 (*tiles)[FTILE],
+                                         unsigned long long *bars) {
+  const int lane = threadIdx.x;
+  float xi[S], yi[S], zi[S], mi[S], ax[S], ay[S], az[S];
+  const int node_off_sink = it.sink_begin;
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    int j = k * 32 + lane;
+    // lanes past the end of the chunk re-use the chunk's first sink (finite numbers, result discarded)
+    float4 s = __ldg(P.src4 + node_off_sink + (j < it.sink_count ? j : 0));
+    xi[k] = s.x; yi[k] = s.y; zi[k] = s.z; mi[k] = s.w;
+    ax[k] = ay[k] = az[k] = 0.f;
+  }
+  Producer pr;
+  pr.ranges = P.ranges; pr.ri = P.range_off[it.node]; pr.rend = P.range_off[it.node + 1];
+  pr.roff = 0; pr.remaining = P.list_len[it.node];
+  const unsigned total = pr.remaining;
+  const unsigned ntiles = (total + FTILE - 1) / FTILE;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < FSTAGES; ++s) produce_tile(pr, P, tiles[s], smem_u32(&bars[s]));
+  }
+  unsigned cnt[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k) cnt[k] = 0;
+  for (unsigned t = 0; t < ntiles; ++t) {
+    const int stage = t % FSTAGES;
+    const unsigned parity = (t / FSTAGES) & 1u;
+    mbar_wait(smem_u32(&bars[stage]), parity);
+    const unsigned nsrc = (t + 1 == ntiles) ? (total - t * FTILE) : (unsigned)FTILE;
+    const float4 *tile = tiles[stage];
+    unsigned j = 0;
+    for (; j + 4 <= nsrc; j += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) interact<S, NC, LAW, GUARD0, COUNT>(tile[j + u], xi, yi, zi, ax, ay, az, P, cnt);
+    }
+    for (; j < nsrc; ++j) interact<S, NC, LAW, GUARD0, COUNT>(tile[j], xi, yi, zi, ax, ay, az, P, cnt);
+    __syncwarp();                       // every lane is done reading this stage
+    if (lane == 0) produce_tile(pr, P, tiles[stage], smem_u32(&bars[stage]));
+  }
+  // kick: v += fcoeff * m_i * a   (RCBForceTree.cxx:594-596 / :615-617)
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    int j = k * 32 + lane;
+    if (j < it.sink_count) {
+      int g = node_off_sink + j;
+      float c = P.fcoeff * mi[k];
+      P.vx[g] = fmaf(c, ax[k], P.vx[g]); P.vy[g] = fmaf(c, ay[k], P.vy[g]); P.vz[g] = fmaf(c, az[k], P.vz[g]);
+    }
+  }
+  if (COUNT) {
+    unsigned long long c64 = 0;   // padded lanes duplicate the chunk's first sink: not counted
+#pragma unroll
+    for (int k = 0; k < S; ++k) c64 += (k * 32 + lane < it.sink_count) ? cnt[k] : 0u;
+    for (int o = 16; o > 0; o >>= 1) c64 += __shfl_down_sync(0xffffffffu, c64, o);
+    if (lane == 0) atomicAdd(P.incut, c64);
+  }
+}
+
+template <int NC, int LAW, bool GUARD0, bool COUNT>
+__global__ void __launch_bounds__(32) k_force(const __grid_constant__ ForceParams P, int n_items) {
+  __shared__ __align__(128) float4 tiles[FSTAGES][FTILE];
+  __shared__ __align__(8) unsigned long long bars[FSTAGES];
+  const int item = blockIdx.x;
+  if (item >= n_items) return;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < FSTAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const WorkItem it = P.items[item];
+  const int S = (it.sink_count + 31) / 32;
+  switch (S) {
+    case 1: run_item<1, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    case 2: run_item<2, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    case 3: run_item<3, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    case 4: run_item<4, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    case 5: run_item<5, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    case 6: run_item<6, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    case 7: run_item<7, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    default: run_item<8, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+  }
+}
+
+// ---- work items: each sink leaf is cut into equal chunks of <= 32*SMAX_ sinks ---------------------------
+__global__ void k_item_count(const Node *__restrict__ nodes, const unsigned *__restrict__ n_ranges, int n_nodes,
+                             unsigned *__restrict__ item_cnt) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_nodes) return;
+  unsigned c = 0;
+  if (n_ranges[k] > 0) c = (unsigned)((nodes[k].count + 32 * SMAX_ - 1) / (32 * SMAX_));
+  item_cnt[k] = c;
+}
+__global__ void k_item_fill(const Node *__restrict__ nodes, const unsigned *__restrict__ item_cnt,
+                            const unsigned *__restrict__ item_off, int n_nodes, WorkItem *__restrict__ items) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_nodes) return;
+  unsigned c = item_cnt[k];
+  if (c == 0) return;
+  int cnt = nodes[k].count, off = nodes[k].offset;
+  int per = (cnt + (int)c - 1) / (int)c;          // balanced chunks
+  per = (per + 31) & ~31;                          // whole 32-sink groups, except the last chunk
+  for (unsigned q = 0; q < c; ++q) {
+    WorkItem w;
+    w.node = k; w.sink_begin = off + (int)q * per;
+    int left = cnt - (int)q * per;
+    w.sink_count = left < per ? left : per;
+    if (w.sink_count < 0) w.sink_count = 0;
+    w.pad = 0;
+    items[item_off[k] + q] = w;
+  }
+}
+
+template <int NC, int LAW, bool GUARD0>
+static int launch_force(haccsr_ctx *c, const ForceParams &P, int n_items, bool count) {
+  if (count) k_force<NC, LAW, GUARD0, true><<<n_items, 32, 0, c->stream>>>(P, n_items);
+  else k_force<NC, LAW, GUARD0, false><<<n_items, 32, 0, c->stream>>>(P, n_items);
+  c->launches++; c->force_launches++;
+  HSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *st) {
+  cudaStream_t s = c->stream;
+  const int nn = c->n_nodes;
+  HSR_TRY(c->item_cnt.ensure(nn + 1)); HSR_TRY(c->item_off.ensure(nn + 1));
+  k_item_count<<<(nn + 255) / 256, 256, 0, s>>>(c->nodes.p, c->n_ranges.p, nn, c->item_cnt.p);
+  c->launches++;
+  HSR_TRY(scan_exclusive(c, c->item_cnt.p, c->item_off.p, nn, c->d_counters + 10));
+  HSR_CUDA(cudaMemsetAsync(c->d_counters + 11, 0, sizeof(unsigned long long), s));
+  HSR_CUDA(cudaMemcpyAsync(c->h_counters + 10, c->d_counters + 10, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  HSR_CUDA(cudaStreamSynchronize(s));
+  c->n_items = c->h_counters[10];
+  if (c->n_items > 0x7fffffffll) { set_error("too many force work items"); return 1; }
+  if (c->n_items == 0) return 0;
+  HSR_TRY(c->items.ensure((size_t)c->n_items));
+  k_item_fill<<<(nn + 255) / 256, 256, 0, s>>>(c->nodes.p, c->item_cnt.p, c->item_off.p, nn, c->items.p);
+  c->launches++;
+
+  ForceParams P;
+  P.items = c->items.p; P.range_off = c->range_off.p; P.ranges = c->ranges.p; P.list_len = c->list_len.p;
+  P.src4 = c->src4.p; P.pool = c->pool.p;
+  P.vx = c->cur.vx; P.vy = c->cur.vy; P.vz = c->cur.vz;
+  P.incut = c->d_counters + 11;
+  for (int i = 0; i < 7; ++i) P.a[i] = c->law.a[i];
+  P.rsm2 = c->law.rsm2; P.rmax2 = c->law.rmax2; P.fcoeff = fcoeff;
+  const int ni = (int)c->n_items;
+  int rc;
+  if (c->law.kind == HACCSR_LAW_NEWTON) rc = launch_force<1, 1, true>(c, P, ni, count_in_cutoff);
+  else {
+    const bool guard = !(c->law.rsm2 > 0.0f);
+    if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false>(c, P, ni, count_in_cutoff);
+    else rc = guard ? launch_force<7, 0, true>(c, P, ni, count_in_cutoff) : launch_force<7, 0, false>(c, P, ni, count_in_cutoff);
+  }
+  if (rc) return rc;
+  if (count_in_cutoff && st) {
+    HSR_CUDA(cudaMemcpyAsync(c->h_counters + 11, c->d_counters + 11, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    HSR_CUDA(cudaStreamSynchronize(s));
+    st->pairs_in_cutoff = (uint64_t)c->h_counters[11];
+  }
+  return 0;
+}
+
+}  // namespace haccsr

@@ -1,0 +1,584 @@
+// tree_build.cu -- device build of the RCB force tree (level-synchronous), sm_100a.
+//
+// What it computes is the tree of the reference's createRCBForceTree
+// (reference src/halo_finder/RCBForceTree.cxx:778-918): every node gets the TIGHT bounding box and the
+// mass-weighted centroid of its particles (cm, src/halo_finder/BGQCM.c:181-212); a node with more than
+// ppn particles is cut on the longest edge of that box (:838-852) at the centroid coordinate (:720),
+// particles with key < pivot going left (:640); a split that leaves one side empty keeps the node as an
+// oversized leaf with two orphan children (:727-729).
+//
+// How it is computed is not the reference's recursion.  All nodes of one level are processed together by
+// passes over fixed 1024-particle tiles (HBM-bound streaming kernels):
+//   A  k_cm_tile        per-tile partial box / centroid sums -> per-node accumulators
+//   B  k_level_finalize  one block: box, centroid, split decision, BFS child allocation (prefix scan)
+//   C1 k_left_count     per-tile count of "goes left" flags + local prefixes at node boundaries
+//   C2 k_scan           exclusive scan of tile counts  => global prefix L(i) of left flags
+//   B2 k_set_children   per node: is = L(end) - L(begin); child counts / offsets; degenerate splits
+//   C3 k_scatter        stable two-way partition of (x,y,z,m | index) records into the other buffer;
+//                       particles of finished leaves are written once to the final tree-order arrays.
+// The centroid sums are accumulated as 128-bit fixed-point integers, so they are exact and independent
+// of summation order: the build is deterministic, and the float centroid equals the reference's
+// (double-accumulated) one except where the reference's own rounding error straddles a float boundary.
+// Children are numbered breadth-first (parent index < child index, as the reference guarantees at :808-809).
+// Left blocks keep input order like the reference; right blocks are kept stable too (the reference's
+// right-block order is an artefact of its swap loop and only affects FP32 summation order).
+#include "common.cuh"
+
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+
+namespace haccsr {
+
+static constexpr int TILE = 1024;      // particles per tile / thread block
+static constexpr int TPB = 256;        // threads per block in tile kernels
+static constexpr int IPT = TILE / TPB; // items per thread (striped: i = base + j*TPB + t)
+static constexpr int SMAX = 32;        // node runs per tile accumulated in shared memory
+
+// ---- helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned enc_f(float f) {   // order-preserving float -> uint
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ void add128(unsigned long long *lo, unsigned long long *hi, long long v) {
+  if (v == 0) return;
+  unsigned long long uv = (unsigned long long)v;
+  unsigned long long old = atomicAdd(lo, uv);
+  unsigned long long carry = (old + uv < old) ? 1ull : 0ull;
+  unsigned long long h = carry + (v < 0 ? ~0ull : 0ull);
+  if (h) atomicAdd(hi, h);
+}
+__device__ __forceinline__ double to_double128(unsigned long long lo, unsigned long long hi) {
+  // two's-complement 128-bit -> double via the magnitude (avoids cancellation for small negative sums)
+  bool neg = (hi >> 63) != 0;
+  if (neg) { lo = ~lo + 1ull; hi = ~hi + (lo == 0 ? 1ull : 0ull); }
+  double d = (double)hi * 18446744073709551616.0 + (double)lo;
+  return neg ? -d : d;
+}
+__device__ __forceinline__ float comp(const float4 &r, int d) { return d == 0 ? r.x : (d == 1 ? r.y : r.z); }
+
+// block-wide exclusive scan of one int per thread (TPB or 1024 threads); returns exclusive prefix,
+// total in *total.  s_w must hold >= 33 ints.
+__device__ __forceinline__ int block_excl_scan(int v, int *s_w, int *total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  __syncthreads();   // protect s_w from the previous use
+  if (lane == 31) s_w[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int x = (lane < nw) ? s_w[lane] : 0;
+    int xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) xi += y;
+    }
+    s_w[lane] = xi - x;          // exclusive warp offsets
+    if (lane == 31) s_w[32] = xi;
+  }
+  __syncthreads();
+  *total = s_w[32];
+  return s_w[w] + inc - v;
+}
+
+// ---- records + maxima ------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_init_records(const float *__restrict__ x, const float *__restrict__ y,
+                                                      const float *__restrict__ z, const float *__restrict__ m,
+                                                      int n, float4 *__restrict__ rec, unsigned *__restrict__ idx,
+                                                      int *__restrict__ nid, unsigned *__restrict__ maxima) {
+  float mc = 0.f, mm = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 r = make_float4(x[i], y[i], z[i], m[i]);
+    rec[i] = r; idx[i] = (unsigned)i; nid[i] = 0;
+    mc = fmaxf(mc, fmaxf(fabsf(r.x), fmaxf(fabsf(r.y), fabsf(r.z))));
+    mm = fmaxf(mm, fabsf(r.w));
+  }
+  unsigned uc = __reduce_max_sync(0xffffffffu, __float_as_uint(mc));
+  unsigned um = __reduce_max_sync(0xffffffffu, __float_as_uint(mm));
+  if ((threadIdx.x & 31) == 0) { atomicMax(&maxima[0], uc); atomicMax(&maxima[1], um); }
+}
+
+// scales[0] = 2^kx applied to float products w*x, scales[1] = 2^km applied to w (both exact powers of two)
+__global__ void k_root_init(Node *nodes, NodeAcc *acc, int n, float3 lo, float3 hi, const unsigned *maxima,
+                            float *scales, LevelInfo *info) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Node r;
+  r.count = n; r.offset = 0; r.cl = 0; r.cr = 0;
+  r.xmin[0] = lo.x; r.xmin[1] = lo.y; r.xmin[2] = lo.z;
+  r.xmax[0] = hi.x; r.xmax[1] = hi.y; r.xmax[2] = hi.z;
+  r.xc[0] = r.xc[1] = r.xc[2] = 0.f; r.ppm = 0.f; r.parent = -1; r.split = -1;
+  nodes[0] = r;
+  NodeAcc a;
+  for (int k = 0; k < 3; ++k) { a.umin[k] = 0xffffffffu; a.umax[k] = 0u; }
+  for (int k = 0; k < 4; ++k) { a.lo[k] = 0; a.hi[k] = 0; }
+  acc[0] = a;
+  float mc = __uint_as_float(maxima[0]), mm = __uint_as_float(maxima[1]);
+  int ec = 0, em = 0;
+  if (mc > 0.f) frexpf(mc, &ec);
+  if (mm > 0.f) frexpf(mm, &em);
+  int kx = 50 - (ec + em), km = 50 - em;
+  kx = max(-100, min(100, kx)); km = max(-100, min(100, km));
+  scales[0] = ldexpf(1.0f, kx); scales[1] = ldexpf(1.0f, km);
+  scales[2] = (float)(km - kx);   // exponent to undo: xc = (Sx / Sw) * 2^(km-kx)
+  info->begin = 0; info->end = 1; info->nsplit = 0; info->error = 0;
+}
+
+// ---- pass A: per-tile partial sums ---------------------------------------------------------------
+struct Part {
+  unsigned umin[3], umax[3];
+  long long s[4];
+};
+__device__ __forceinline__ void part_reset(Part &p) {
+  p.umin[0] = p.umin[1] = p.umin[2] = 0xffffffffu; p.umax[0] = p.umax[1] = p.umax[2] = 0u;
+  p.s[0] = p.s[1] = p.s[2] = p.s[3] = 0;
+}
+__device__ __forceinline__ void part_add(Part &p, const float4 &r, float sx, float sm) {
+  unsigned ex = enc_f(r.x), ey = enc_f(r.y), ez = enc_f(r.z);
+  p.umin[0] = min(p.umin[0], ex); p.umax[0] = max(p.umax[0], ex);
+  p.umin[1] = min(p.umin[1], ey); p.umax[1] = max(p.umax[1], ey);
+  p.umin[2] = min(p.umin[2], ez); p.umax[2] = max(p.umax[2], ez);
+  // the product w*x is formed in float exactly as in BGQCM.c:203-206, then summed exactly
+  p.s[0] += __float2ll_rn(__fmul_rn(__fmul_rn(r.w, r.x), sx));
+  p.s[1] += __float2ll_rn(__fmul_rn(__fmul_rn(r.w, r.y), sx));
+  p.s[2] += __float2ll_rn(__fmul_rn(__fmul_rn(r.w, r.z), sx));
+  p.s[3] += __float2ll_rn(__fmul_rn(r.w, sm));
+}
+
+struct Slot {
+  unsigned umin[3], umax[3];
+  unsigned used, pad;
+  unsigned long long s[4];
+};
+
+__device__ __forceinline__ void flush_part(const Part &p, int nd, int n0, Slot *slots, NodeAcc *acc) {
+  int sl = nd - n0;
+  if (sl >= 0 && sl < SMAX) {
+    Slot &S = slots[sl];
+    for (int k = 0; k < 3; ++k) { atomicMin(&S.umin[k], p.umin[k]); atomicMax(&S.umax[k], p.umax[k]); }
+    for (int k = 0; k < 4; ++k) atomicAdd(&S.s[k], (unsigned long long)p.s[k]);
+    S.used = 1;
+  } else {
+    NodeAcc &A = acc[nd];
+    for (int k = 0; k < 3; ++k) { atomicMin(&A.umin[k], p.umin[k]); atomicMax(&A.umax[k], p.umax[k]); }
+    for (int k = 0; k < 4; ++k) add128(&A.lo[k], &A.hi[k], p.s[k]);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) k_cm_tile(const float4 *__restrict__ rec, const int *__restrict__ nid, int n,
+                                                 NodeAcc *__restrict__ acc, const float *__restrict__ scales) {
+  __shared__ int s_n0;
+  __shared__ Slot slots[SMAX];
+  const int t = threadIdx.x, base = blockIdx.x * TILE;
+  if (t == 0) s_n0 = INT_MAX;
+  if (t < SMAX) {
+    Slot &S = slots[t];
+    S.umin[0] = S.umin[1] = S.umin[2] = 0xffffffffu; S.umax[0] = S.umax[1] = S.umax[2] = 0u;
+    S.used = 0; S.s[0] = S.s[1] = S.s[2] = S.s[3] = 0;
+  }
+  __syncthreads();
+  float4 r[IPT]; int nd[IPT];
+  int mn = INT_MAX;
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) {
+    int i = base + j * TPB + t;
+    nd[j] = (i < n) ? nid[i] : -1;
+    if (nd[j] >= 0) { r[j] = rec[i]; mn = min(mn, nd[j]); }
+  }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  if ((t & 31) == 0 && mn != INT_MAX) atomicMin(&s_n0, mn);
+  __syncthreads();
+  const int n0 = s_n0;
+  if (n0 == INT_MAX) return;   // no active particle in this tile
+  const float sx = scales[0], sm = scales[1];
+
+  // fast path: the whole warp (all its items) belongs to one node -> one shuffle reduction
+  int first = nd[0];
+  bool same = true;
+#pragma unroll
+  for (int j = 1; j < IPT; ++j) same = same && (nd[j] == first);
+  int f0 = __shfl_sync(0xffffffffu, first, 0);
+  bool uni = __all_sync(0xffffffffu, same && first == f0 && first >= 0);
+  if (uni) {
+    Part p; part_reset(p);
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) part_add(p, r[j], sx, sm);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      p.umin[k] = __reduce_min_sync(0xffffffffu, p.umin[k]);
+      p.umax[k] = __reduce_max_sync(0xffffffffu, p.umax[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) p.s[k] += __shfl_down_sync(0xffffffffu, p.s[k], o);
+    }
+    if ((t & 31) == 0) flush_part(p, f0, n0, slots, acc);
+  } else {
+    // slow path: per-thread runs (integer atomics keep the result order-independent)
+    Part p; part_reset(p);
+    int cur = -1;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      if (nd[j] != cur) {
+        if (cur >= 0) flush_part(p, cur, n0, slots, acc);
+        part_reset(p); cur = nd[j];
+      }
+      if (nd[j] >= 0) part_add(p, r[j], sx, sm);
+    }
+    if (cur >= 0) flush_part(p, cur, n0, slots, acc);
+  }
+  __syncthreads();
+  if (t < SMAX && slots[t].used) {
+    NodeAcc &A = acc[n0 + t];
+    const Slot &S = slots[t];
+    for (int k = 0; k < 3; ++k) { atomicMin(&A.umin[k], S.umin[k]); atomicMax(&A.umax[k], S.umax[k]); }
+    for (int k = 0; k < 4; ++k) add128(&A.lo[k], &A.hi[k], (long long)S.s[k]);
+  }
+}
+
+// ---- pass B: finalize the nodes of one level, decide splits, allocate children breadth-first ----------
+__global__ void __launch_bounds__(1024) k_level_finalize(Node *__restrict__ nodes, NodeAcc *__restrict__ acc,
+                                                         int begin, int end, int next_base, int max_nodes,
+                                                         int ppn, const float *__restrict__ scales,
+                                                         LevelInfo *__restrict__ info) {
+  __shared__ int s_w[34];
+  __shared__ int s_err;
+  if (threadIdx.x == 0) s_err = 0;
+  int running = 0;
+  const double undo = ldexp(1.0, (int)scales[2]);
+  for (int b = begin; b < end; b += blockDim.x) {
+    int k = b + threadIdx.x;
+    bool valid = k < end;
+    int split = 0, d = -1;
+    Node nd;
+    if (valid) {
+      nd = nodes[k];
+      if (nd.count > 0) {
+        NodeAcc a = acc[k];
+        for (int q = 0; q < 3; ++q) { nd.xmin[q] = dec_f(a.umin[q]); nd.xmax[q] = dec_f(a.umax[q]); }
+        double sw = to_double128(a.lo[3], a.hi[3]);
+        for (int q = 0; q < 3; ++q) {
+          double sxq = to_double128(a.lo[q], a.hi[q]);
+          nd.xc[q] = (float)((sxq / sw) * undo);                       // BGQCM.c:209-211
+        }
+        if (nd.count > ppn) {                                          // RCBForceTree.cxx:788
+          float l0 = __fsub_rn(nd.xmax[0], nd.xmin[0]), l1 = __fsub_rn(nd.xmax[1], nd.xmin[1]),
+                l2 = __fsub_rn(nd.xmax[2], nd.xmin[2]);
+          d = (l0 > l1 && l0 > l2) ? 0 : ((l1 > l2) ? 1 : 2);          // :844-852
+          split = 1;
+        } else {
+          // leaf monopole: sum of masses (pp<1>, :536-569); unused when count <= 1 (:788-797)
+          nd.ppm = (nd.count > 1) ? (float)(sw / (double)scales[1]) : 0.f;
+        }
+      }
+      nd.split = split ? d : -1;
+    }
+    int total;
+    int rank = block_excl_scan(split, s_w, &total);
+    if (valid) {
+      if (split) {
+        int cl = next_base + 2 * (running + rank);
+        if (cl + 1 >= max_nodes) { s_err = 1; nd.split = -1; }
+        else {
+          nd.cl = cl; nd.cr = cl + 1;     // provisional; cleared by k_set_children on a degenerate split
+          Node c;
+          c.count = 0; c.offset = 0; c.cl = 0; c.cr = 0; c.ppm = 0.f; c.parent = k; c.split = -1;
+          for (int q = 0; q < 3; ++q) { c.xmin[q] = nd.xmin[q]; c.xmax[q] = nd.xmax[q]; c.xc[q] = 0.f; }
+          Node l = c, r = c;
+          l.xmax[d] = nd.xc[d]; r.xmin[d] = nd.xc[d];                  // :747,763
+          nodes[cl] = l; nodes[cl + 1] = r;
+          NodeAcc z;
+          for (int q = 0; q < 3; ++q) { z.umin[q] = 0xffffffffu; z.umax[q] = 0u; }
+          for (int q = 0; q < 4; ++q) { z.lo[q] = 0; z.hi[q] = 0; }
+          acc[cl] = z; acc[cl + 1] = z;
+        }
+      }
+      nodes[k] = nd;
+    }
+    running += total;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ns = s_err ? 0 : running;
+    info->begin = next_base; info->end = next_base + 2 * ns; info->nsplit = ns; info->error = s_err;
+  }
+}
+
+// ---- shared by C1 and C3: left flags of a tile and their exclusive prefix in particle order --------------
+struct ItemInfo { int nd, sp, flag, excl; };
+
+__device__ __forceinline__ int tile_flags_scan(const float4 *__restrict__ rec, const int *__restrict__ nid,
+                                               const Node *__restrict__ nodes, int n, int base, ItemInfo it[IPT],
+                                               float4 r[IPT], bool load_rec, int *s_w) {
+  const int t = threadIdx.x;
+  int carry = 0;
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) {
+    int i = base + j * TPB + t;
+    int nd = (i < n) ? nid[i] : -1;
+    int sp = -1, flag = 0;
+    if (nd >= 0) {
+      sp = nodes[nd].split;
+      if (load_rec) r[j] = rec[i];
+      if (sp >= 0) {
+        float key = load_rec ? comp(r[j], sp) : reinterpret_cast<const float *>(rec)[4 * (size_t)i + sp];
+        flag = key < nodes[nd].xc[sp];                                 // RCBForceTree.cxx:640, pivot :720
+      }
+    }
+    int total;
+    int e = block_excl_scan(flag, s_w, &total);
+    it[j].nd = nd; it[j].sp = sp; it[j].flag = flag; it[j].excl = carry + e;
+    carry += total;
+  }
+  return carry;
+}
+
+__global__ void __launch_bounds__(TPB) k_left_count(const float4 *__restrict__ rec, const int *__restrict__ nid,
+                                                    const Node *__restrict__ nodes, int n,
+                                                    unsigned *__restrict__ tilecount, int *__restrict__ lstart,
+                                                    int *__restrict__ lend) {
+  __shared__ int s_w[34];
+  ItemInfo it[IPT]; float4 r[IPT];
+  const int base = blockIdx.x * TILE;
+  int total = tile_flags_scan(rec, nid, nodes, n, base, it, r, false, s_w);
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) {
+    if (it[j].sp >= 0) {
+      int i = base + j * TPB + threadIdx.x;
+      int off = nodes[it[j].nd].offset, cnt = nodes[it[j].nd].count;
+      if (i == off) lstart[it[j].nd] = it[j].excl;
+      if (i == off + cnt - 1) lend[it[j].nd] = it[j].excl + it[j].flag;
+    }
+  }
+  if (threadIdx.x == 0) tilecount[blockIdx.x] = (unsigned)total;
+}
+
+// single-block exclusive scan (n up to a few million; used on per-tile and per-node counts)
+__global__ void __launch_bounds__(1024) k_scan(const unsigned *__restrict__ in, unsigned *__restrict__ out,
+                                               long long n, unsigned long long *__restrict__ d_total) {
+  __shared__ int s_w[34];
+  unsigned long long running = 0;
+  for (long long b = 0; b < n; b += blockDim.x) {
+    long long i = b + threadIdx.x;
+    int v = (i < n) ? (int)in[i] : 0;
+    int total;
+    int e = block_excl_scan(v, s_w, &total);
+    if (i < n) out[i] = (unsigned)(running + (unsigned long long)e);
+    running += (unsigned long long)(unsigned)total;
+  }
+  if (threadIdx.x == 0 && d_total) *d_total = running;
+}
+
+__global__ void k_set_children(Node *__restrict__ nodes, int begin, int end, const unsigned *__restrict__ tilebase,
+                               const int *__restrict__ lstart, const int *__restrict__ lend,
+                               int *__restrict__ lbase, int *__restrict__ nleft) {
+  int k = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= end) return;
+  Node nd = nodes[k];
+  if (nd.split < 0) return;
+  int ts = nd.offset / TILE, te = (nd.offset + nd.count - 1) / TILE;
+  int Ls = (int)tilebase[ts] + lstart[k], Le = (int)tilebase[te] + lend[k];
+  int is = Le - Ls;
+  if (is == 0 || is == nd.count) {
+    // degenerate split (RCBForceTree.cxx:727-729): the node stays a leaf, its two children stay empty
+    // orphans, and its monopole mass is the sum over those empty children, i.e. zero (:856-889).
+    // nodes[k].split keeps the dimension for the rest of this level so that k_scatter recomputes the
+    // same left flags k_left_count counted; nleft = -1 marks the node as finished.
+    nodes[k].cl = 0; nodes[k].cr = 0; nodes[k].ppm = 0.f; nleft[k] = -1;
+    return;
+  }
+  lbase[k] = Ls; nleft[k] = is;
+  nodes[nd.cl].count = is;            nodes[nd.cl].offset = nd.offset;         // :731-746
+  nodes[nd.cr].count = nd.count - is; nodes[nd.cr].offset = nd.offset + is;    // :732,762
+}
+
+__global__ void __launch_bounds__(TPB) k_scatter(const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
+                                                 const int *__restrict__ nid, const Node *__restrict__ nodes, int n,
+                                                 const unsigned *__restrict__ tilebase, const int *__restrict__ lbase,
+                                                 const int *__restrict__ nleft, float4 *__restrict__ rec_out,
+                                                 unsigned *__restrict__ idx_out, int *__restrict__ nid_out,
+                                                 float4 *__restrict__ src4, unsigned *__restrict__ perm) {
+  __shared__ int s_w[34];
+  ItemInfo it[IPT]; float4 r[IPT];
+  const int base = blockIdx.x * TILE;
+  tile_flags_scan(rec, nid, nodes, n, base, it, r, true, s_w);
+  const int tb = (int)tilebase[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) {
+    int i = base + j * TPB + threadIdx.x;
+    if (i >= n) continue;
+    int nd = it[j].nd;
+    if (nd < 0) { nid_out[i] = -1; continue; }
+    int sp = it[j].sp;
+    if (sp < 0 || nleft[nd] < 0) {   // finished leaf (or degenerate split): final position reached
+      src4[i] = r[j]; perm[i] = idx[i]; nid_out[i] = -1;
+      continue;
+    }
+    int off = nodes[nd].offset;
+    int L = tb + it[j].excl - lbase[nd];       // left flags of this node before i
+    int dest, child;
+    if (it[j].flag) { dest = off + L; child = nodes[nd].cl; }
+    else { dest = off + nleft[nd] + ((i - off) - L); child = nodes[nd].cr; }
+    rec_out[dest] = r[j]; idx_out[dest] = idx[i]; nid_out[dest] = child;
+  }
+}
+
+// ---- monopole moments of internal nodes, bottom-up one level at a time (RCBForceTree.cxx:856-889) -------
+__global__ void k_moments(Node *__restrict__ nodes, const float4 *__restrict__ src4, int begin, int end) {
+  int k = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= end) return;
+  int cl = nodes[k].cl, cr = nodes[k].cr;
+  if (cl == 0 && cr == 0) return;
+  float s = 0.f;
+  int ch[2] = {cl, cr};
+  for (int q = 0; q < 2; ++q) {
+    int c = ch[q];
+    if (c > 0 && nodes[c].count > 0) {
+      float add = (nodes[c].count <= 1) ? src4[nodes[c].offset].w : nodes[c].ppm;
+      s = __fadd_rn(s, add);
+    }
+  }
+  nodes[k].ppm = s;
+}
+
+// ---- permute the caller-visible arrays into tree order (the reference does this in place, :648-669) ------
+__global__ void __launch_bounds__(256) k_gather(Soa in, Soa out, const float4 *__restrict__ src4,
+                                                const unsigned *__restrict__ perm, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned p = perm[i];
+    float4 r = src4[i];
+    out.x[i] = r.x; out.y[i] = r.y; out.z[i] = r.z; out.mass[i] = r.w;
+    out.vx[i] = in.vx[p]; out.vy[i] = in.vy[p]; out.vz[i] = in.vz[p];
+    out.phi[i] = in.phi[p]; out.id[i] = in.id[p]; out.mask[i] = in.mask[p];
+  }
+}
+
+// ---- host orchestration -------------------------------------------------------------------------------
+int scan_exclusive(haccsr_ctx *c, const unsigned *in, unsigned *out, int64_t n, unsigned long long *d_total) {
+  k_scan<<<1, 1024, 0, c->stream>>>(in, out, (long long)n, d_total);
+  c->launches++;
+  HSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3], int64_t ppn64) {
+  if (n64 >= (int64_t)INT_MAX - 2 * TILE) { set_error("too many particles for 32-bit indexing: %lld", (long long)n64); return 1; }
+  const int n = (int)n64;
+  const int ppn = (int)(ppn64 > INT_MAX ? INT_MAX : ppn64);
+  cudaStream_t st = c->stream;
+  const int ntiles = (n + TILE - 1) / TILE;
+  // node pool: every split node has > ppn particles and two non-empty children, so nodes <= 2N-1; in
+  // practice ~4N/ppn.  Start generously and grow (rebuild) if the pool runs out.
+  int64_t want_nodes = 1024 + 8 * (n64 / (ppn > 0 ? ppn : 1));
+  if (want_nodes > 2 * n64 + 8) want_nodes = 2 * n64 + 8;
+  if ((int64_t)c->nodes.cap > want_nodes) want_nodes = (int64_t)c->nodes.cap;
+
+  HSR_TRY(c->recA.ensure(n + 1)); HSR_TRY(c->recB.ensure(n + 1)); HSR_TRY(c->src4.ensure(n + 1));
+  HSR_TRY(c->idxA.ensure(n + 1)); HSR_TRY(c->idxB.ensure(n + 1)); HSR_TRY(c->perm.ensure(n + 1));
+  HSR_TRY(c->nidA.ensure(n + 1)); HSR_TRY(c->nidB.ensure(n + 1));
+  HSR_TRY(c->tilecount.ensure(ntiles + 1)); HSR_TRY(c->tilebase.ensure(ntiles + 1));
+  HSR_TRY(c->scratch_u32.ensure(16));
+
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    HSR_TRY(c->nodes.ensure(want_nodes)); HSR_TRY(c->acc.ensure(want_nodes));
+    HSR_TRY(c->lstart.ensure(want_nodes)); HSR_TRY(c->lend.ensure(want_nodes));
+    HSR_TRY(c->lbase.ensure(want_nodes)); HSR_TRY(c->nleft.ensure(want_nodes));
+    const int max_nodes = (int)(c->nodes.cap > (size_t)INT_MAX ? INT_MAX : c->nodes.cap);
+    unsigned *maxima = c->scratch_u32.p;
+    float *scales = reinterpret_cast<float *>(c->scratch_u32.p + 4);
+    HSR_CUDA(cudaMemsetAsync(maxima, 0, 4 * sizeof(unsigned), st));
+    c->n_tree = n; c->n_nodes = 1; c->n_levels = 0;
+    if (n == 0) {
+      k_root_init<<<1, 1, 0, st>>>(c->nodes.p, c->acc.p, 0, make_float3(lo[0], lo[1], lo[2]),
+                                   make_float3(hi[0], hi[1], hi[2]), maxima, scales, c->d_level);
+      c->launches++;
+      HSR_CUDA(cudaGetLastError());
+      c->level_begin[0] = 0; c->level_end[0] = 1; c->n_levels = 1;
+      return 0;
+    }
+    int grid_lin = (n + TPB - 1) / TPB;
+    if (grid_lin > c->sm_count * 16) grid_lin = c->sm_count * 16;
+    k_init_records<<<grid_lin, TPB, 0, st>>>(c->cur.x, c->cur.y, c->cur.z, c->cur.mass, n, c->recA.p, c->idxA.p,
+                                             c->nidA.p, maxima);
+    k_root_init<<<1, 1, 0, st>>>(c->nodes.p, c->acc.p, n, make_float3(lo[0], lo[1], lo[2]),
+                                 make_float3(hi[0], hi[1], hi[2]), maxima, scales, c->d_level);
+    c->launches += 2;
+    HSR_CUDA(cudaGetLastError());
+
+    float4 *rec = c->recA.p, *rec_o = c->recB.p;
+    unsigned *idx = c->idxA.p, *idx_o = c->idxB.p;
+    int *nid = c->nidA.p, *nid_o = c->nidB.p;
+    int begin = 0, end = 1, nnodes = 1, level = 0;
+    bool overflow = false;
+    for (;; ++level) {
+      if (level >= 127) { set_error("tree deeper than 127 levels"); return 1; }
+      c->level_begin[level] = begin; c->level_end[level] = end;
+      k_cm_tile<<<ntiles, TPB, 0, st>>>(rec, nid, n, c->acc.p, scales);
+      k_level_finalize<<<1, 1024, 0, st>>>(c->nodes.p, c->acc.p, begin, end, nnodes, max_nodes, ppn, scales, c->d_level);
+      c->launches += 2;
+      HSR_CUDA(cudaMemcpyAsync(c->h_level, c->d_level, sizeof(LevelInfo), cudaMemcpyDeviceToHost, st));
+      HSR_CUDA(cudaStreamSynchronize(st));
+      LevelInfo li = *c->h_level;
+      if (li.error) { overflow = true; break; }
+      if (li.nsplit > 0) {
+        k_left_count<<<ntiles, TPB, 0, st>>>(rec, nid, c->nodes.p, n, c->tilecount.p, c->lstart.p, c->lend.p);
+        c->launches++;
+        HSR_TRY(scan_exclusive(c, c->tilecount.p, c->tilebase.p, ntiles, nullptr));
+        int nl = end - begin;
+        k_set_children<<<(nl + 255) / 256, 256, 0, st>>>(c->nodes.p, begin, end, c->tilebase.p, c->lstart.p,
+                                                          c->lend.p, c->lbase.p, c->nleft.p);
+        c->launches++;
+      }
+      k_scatter<<<ntiles, TPB, 0, st>>>(rec, idx, nid, c->nodes.p, n, c->tilebase.p, c->lbase.p, c->nleft.p, rec_o,
+                                        idx_o, nid_o, c->src4.p, c->perm.p);
+      c->launches++;
+      HSR_CUDA(cudaGetLastError());
+      nnodes = li.end;
+      if (li.nsplit == 0) break;
+      begin = li.begin; end = li.end;
+      float4 *tr = rec; rec = rec_o; rec_o = tr;
+      unsigned *ti = idx; idx = idx_o; idx_o = ti;
+      int *tn = nid; nid = nid_o; nid_o = tn;
+    }
+    if (overflow) {
+      if ((int64_t)c->nodes.cap >= 2 * n64 + 8) { set_error("node pool exhausted at its upper bound"); return 1; }
+      want_nodes = (int64_t)c->nodes.cap * 2;
+      if (want_nodes > 2 * n64 + 8) want_nodes = 2 * n64 + 8;
+      // DevBuf::ensure reallocates (contents are rebuilt from scratch on the next attempt)
+      continue;
+    }
+    c->n_nodes = nnodes; c->n_levels = level + 1;
+    for (int L = c->n_levels - 2; L >= 0; --L) {
+      int nl = c->level_end[L] - c->level_begin[L];
+      k_moments<<<(nl + 255) / 256, 256, 0, st>>>(c->nodes.p, c->src4.p, c->level_begin[L], c->level_end[L]);
+      c->launches++;
+    }
+    k_gather<<<grid_lin, 256, 0, st>>>(c->cur, c->alt, c->src4.p, c->perm.p, n);
+    c->launches++;
+    HSR_CUDA(cudaGetLastError());
+    // particles beyond n (out-of-box tail) keep their place: copy them across so cur/alt can be swapped
+    if (c->n_resident > n) {
+      size_t m = (size_t)(c->n_resident - n);
+      Soa &a = c->cur, &b = c->alt;
+      float *fa[8] = {a.x, a.y, a.z, a.vx, a.vy, a.vz, a.mass, a.phi};
+      float *fb[8] = {b.x, b.y, b.z, b.vx, b.vy, b.vz, b.mass, b.phi};
+      for (int q = 0; q < 8; ++q) HSR_CUDA(cudaMemcpyAsync(fb[q] + n, fa[q] + n, m * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      HSR_CUDA(cudaMemcpyAsync(b.id + n, a.id + n, m * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+      HSR_CUDA(cudaMemcpyAsync(b.mask + n, a.mask + n, m * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
+    }
+    Soa tmp = c->cur; c->cur = c->alt; c->alt = tmp;
+    return 0;
+  }
+  set_error("tree build did not converge on a node pool size");
+  return 1;
+}
+
+}  // namespace haccsr

@@ -1,0 +1,150 @@
+/* include/haccsr.h -- C ABI of libhaccsr.so: HACC's short-range RCB-tree force on one B200.
+ *
+ * This is the drop-in boundary for the reference's short-range hot path.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference root).  Plain pointers and sizes
+ * only; all particle arrays use the reference's build types (-DID_64 -DPOSVEL_32 -DGRID_32,
+ * src/halo_finder/include.mk:4 => POSVEL_T=float, ID_T=int64_t, MASK_T=uint16_t,
+ * src/halo_finder/BasicDefinition.h:64-90).
+ *
+ * Life cycle (what RCBForceTree<1>'s constructor does in one call, src/halo_finder/RCBForceTree.cxx:335-450,
+ * split so particles can stay resident on the GPU across the nsub sub-cycles of Particles::subCycle,
+ * src/cpu/Particles.cxx:1176-1201):
+ *
+ *   haccsr_create -> haccsr_set_force_law -> haccsr_upload
+ *        -> nsub x [ haccsr_stream, haccsr_kick, haccsr_stream ] -> haccsr_download -> haccsr_destroy
+ *
+ * There is no CPU fallback: every call fails with a non-zero status if no sm_100 device is usable.
+ * All functions return 0 on success; on failure haccsr_last_error() describes the problem.
+ * A context is bound to one device and must be used from one thread at a time.
+ */
+#ifndef HACCSR_H
+#define HACCSR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HACCSR_VERSION 1
+
+typedef struct haccsr_ctx haccsr_ctx;
+
+/* Force-law kinds.  Replaces the ForceLaw* functor argument of the tree constructor
+ * (src/halo_finder/ForceLaw.h:96-127). */
+enum {
+  /* ForceLawSR over a polynomial grid force: f(r2) = (r2+rsm^2)^-3/2 - sum_k a[k] r2^k, for r2 < rmax^2
+   * (ForceLaw.cxx:137-141,187-192; BGQStep16.c:167-187).  ncoef <= 7. */
+  HACCSR_LAW_SR_POLY = 0,
+  /* ForceLawNewton: f(r2) = r2^-3/2 (ForceLaw.h:102-107), used when the caller passes fl == NULL
+   * (RCBForceTree.cxx:395-404); pairs with r2 == 0 contribute nothing (the guard of BGQStep16.c:183). */
+  HACCSR_LAW_NEWTON = 3
+};
+
+/* Mirrors RCBForceTree::printStats (RCBForceTree.cxx:460-511) plus the measurement fields of
+ * SURVEY.md section 8(d). */
+typedef struct haccsr_stats {
+  int64_t particles;        /* count handed to the kick                                  */
+  int64_t nodes;            /* tree.size()                                               */
+  int64_t leaves;           /* leaves counted from node 1 on, as printStats does        */
+  int64_t empty_leaves;     /* orphan nodes left by degenerate splits                    */
+  int64_t max_ppn;          /* largest leaf                                              */
+  double  mean_ppn;         /* mean particles per non-empty leaf                         */
+  int64_t levels;           /* depth of the tree                                         */
+  int64_t sink_leaves;      /* leaves that pass the force-box test (RCBForceTree.cxx:1166-1170) */
+  int64_t list_ranges;      /* (start,count) source ranges emitted by the walk           */
+  int64_t pseudo_particles; /* accepted monopoles copied into the pseudo-particle pool   */
+  int64_t max_list;         /* longest interaction list (sources) of any sink leaf       */
+  uint64_t pairs_evaluated; /* sum over sink leaves of count x list length               */
+  uint64_t pairs_in_cutoff; /* pairs with 0 < r2 < rmax^2; only when count_in_cutoff != 0 */
+  float ms_build;           /* device time: tree build incl. permuting the 10 arrays     */
+  float ms_walk;            /* device time: interaction-list construction                */
+  float ms_force;           /* device time: leaf-vs-list force kernel + kick             */
+  float ms_total;           /* device time of the whole haccsr_kick call                 */
+  int32_t force_launches;   /* kernel launches of the force kernel in this call          */
+  int32_t total_launches;   /* all kernel launches in this call                          */
+} haccsr_stats;
+
+/* Per-call options of the kick; zero-initialise for defaults. */
+typedef struct haccsr_kick_opts {
+  int32_t count_in_cutoff;  /* 1: also count pairs with 0 < r2 < rmax^2 (slower kernel variant) */
+  int32_t skip_force;       /* 1: build + walk only (used to time the phases separately)        */
+  int32_t reserved[6];
+} haccsr_kick_opts;
+
+const char *haccsr_last_error(void);
+
+/* Number of CUDA devices with compute capability 10.x visible to this process (0 => unusable). */
+int haccsr_device_count(void);
+
+/* Create a context on `device` able to hold `max_particles` particles.
+ * Replaces: the allocation side of `new RCBMonopoleForceTree(...)` (src/cpu/Particles.cxx:1313) and the
+ * bigchunk node pool (src/halo_finder/bigchunk.h:49-139). */
+int haccsr_create(haccsr_ctx **out, int device, int64_t max_particles);
+int haccsr_destroy(haccsr_ctx *ctx);
+
+/* Run all work of this context on the given CUDA stream (a cudaStream_t passed as void*; NULL = the
+ * context's own stream).  Lets a host framework time the kernels with events on its own stream. */
+int haccsr_set_stream(haccsr_ctx *ctx, void *cuda_stream);
+
+/* Replaces: the `ForceLaw *fl` and `POSVEL_T fsm` (= rmax), `POSVEL_T r` (= rsm) constructor arguments
+ * (src/halo_finder/RCBForceTree.h:113-121). */
+int haccsr_set_force_law(haccsr_ctx *ctx, int kind, const float *coeffs, int ncoef, float rsm, float rmax);
+
+/* Copy `count` particles from host arrays into the context (H2D).
+ * Replaces: handing m_xArr ... m_maskArr to the constructor (src/cpu/Particles.cxx:1317-1327). */
+int haccsr_upload(haccsr_ctx *ctx, int64_t count, const float *x, const float *y, const float *z,
+                  const float *vx, const float *vy, const float *vz, const float *mass, const float *phi,
+                  const int64_t *id, const uint16_t *mask);
+
+/* Copy the context's particles back to host arrays (D2H), in the tree order of the last kick -- the
+ * reference likewise leaves all 10 arrays permuted in place (RCBForceTree.cxx:623-672).  Any pointer
+ * may be NULL to skip that array. */
+int haccsr_download(haccsr_ctx *ctx, int64_t count, float *x, float *y, float *z, float *vx, float *vy,
+                    float *vz, float *mass, float *phi, int64_t *id, uint16_t *mask);
+
+/* Optional: page-lock / unlock a caller-owned host array so upload/download run at full PCIe rate. */
+int haccsr_host_register(void *ptr, size_t bytes);
+int haccsr_host_unregister(void *ptr);
+
+/* The short-range kick on the resident particles: tree build (centre-of-mass recursive bisection,
+ * leaves of <= ppn particles), interaction lists (opening angle theta), leaf-vs-list force kernel;
+ * v += fcoeff * mass_i * sum_j mass_j f(r2) (x_j - x_i) for particles in leaves touching the force box.
+ * Replaces: RCBForceTree<1>::RCBForceTree(...) in full (src/halo_finder/RCBForceTree.cxx:335-450):
+ *   tree_lo/tree_hi   = minLoc/maxLoc, force_lo/force_hi = minForceLoc/maxForceLoc, theta = oa, ppn = nd,
+ *   fcoeff = fcoeff; only the first `count` resident particles take part (Particles.cxx:1248).
+ * tdpts must be 1 (monopole, -R); the quadrupole mode (12) is not implemented and is refused.
+ * stats and opts may be NULL. */
+int haccsr_kick(haccsr_ctx *ctx, int64_t count, const float tree_lo[3], const float tree_hi[3],
+                const float force_lo[3], const float force_hi[3], float theta, int64_t ppn, int tdpts,
+                float fcoeff, const haccsr_kick_opts *opts, haccsr_stats *stats);
+
+/* x += prefactor_tau * v for all resident particles.
+ * Replaces: Particles::map1 (src/cpu/Particles.cxx:732-758); prefactor_tau = prefactor * tau there. */
+int haccsr_stream(haccsr_ctx *ctx, float prefactor_tau);
+
+/* Move particles outside [0,hi)^3 to the tail of the arrays (stable) and report how many remain in front.
+ * Replaces: the out-of-box tail move of Particles::resortParticles (src/cpu/Particles.cxx:402-488,
+ * m_Np_last :443); the per-cell counting sort is not reproduced because the tree re-sorts anyway. */
+int haccsr_partition_in_box(haccsr_ctx *ctx, const float hi[3], int64_t *count_in_box);
+
+/* mass[:] = value for all resident particles.  Replaces: Particles.cxx:1256-1257. */
+int haccsr_fill_mass(haccsr_ctx *ctx, float value);
+
+/* ---- inspection (tests and tools): the tree and the lists of the last kick ---------------------- */
+/* Node table, `cap` entries per array; box10 = xmin[3] xmax[3] xc[3] ppm per node
+ * (TreeNode, src/halo_finder/RCBForceTree.h:131-147).  Returns the node count in *nodes. */
+int haccsr_get_tree(haccsr_ctx *ctx, int64_t cap, int64_t *nodes, int32_t *count, int32_t *offset,
+                    int32_t *cl, int32_t *cr, float *box10);
+/* Interaction lists of the last kick.  For node k: ranges [range_off[k], range_off[k+1]) of
+ * (start,count) pairs.  start < 2^31 indexes particles in tree order; start >= 2^31 indexes the
+ * pseudo-particle pool (start - 2^31).  Query sizes first with cap_* = 0. */
+int haccsr_get_lists(haccsr_ctx *ctx, int64_t cap_nodes, int64_t cap_ranges, int64_t cap_pool,
+                     int64_t *n_nodes, int64_t *n_ranges, int64_t *n_pool, uint32_t *range_off,
+                     uint32_t *ranges /* 2 per entry */, float *pool /* 4 per entry */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HACCSR_H */
