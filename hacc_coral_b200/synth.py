@@ -121,7 +121,7 @@ def zeldovich(ns, z=50.0, seed=5009888, ghost=11, growth_boost=1.0, dtype=np.flo
     disp = []
     for Kc in (KX, KY, KZ):
         # psi_k = i k delta_k / k^2  (div psi = -delta), i.e. x = q - D grad(phi) with laplacian(phi) = delta
-        psi = fft.irfftn(1j * Kc * dk * invk2, s=(ns, ns, ns))
+        psi = fft.irfftn(1j * Kc * dk * invk2, s=(ns, ns, ns), axes=(0, 1, 2))
         disp.append(D * psi / c["spacing"])                      # Mpc/h -> grid units
     g = np.arange(ns, dtype=np.float64) + 0.5
     X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
@@ -142,3 +142,74 @@ def zeldovich(ns, z=50.0, seed=5009888, ghost=11, growth_boost=1.0, dtype=np.flo
     hi = np.float32(ns + 2 * ghost)
     pos = np.minimum(pos, np.nextafter(hi, np.float32(0)))
     return _pack(pos[:, 0], pos[:, 1], pos[:, 2])
+
+
+def zeldovich_torch(ns, z=50.0, seed=5009888, ghost=11, growth_boost=1.0, device="cuda"):
+    """Same recipe as zeldovich() evaluated with torch FFTs on `device` (used by bench.py so that a
+    256^3 snapshot takes seconds).  Returns the usual dict of numpy arrays (host)."""
+    import torch
+    c = COSMO
+    L = ns * c["spacing"]
+    kf = 2.0 * np.pi / L
+    dev = torch.device(device)
+    k1 = torch.fft.fftfreq(ns, d=1.0 / ns, device=dev, dtype=torch.float64) * kf
+    kz = torch.fft.rfftfreq(ns, d=1.0 / ns, device=dev, dtype=torch.float64) * kf
+    KX, KY, KZ = torch.meshgrid(k1, k1, kz, indexing="ij")
+    K2 = KX ** 2 + KY ** 2 + KZ ** 2
+    kt, Tt = load_transfer()
+    K = torch.sqrt(K2).clamp_min(float(kt[0]))
+    # log-log interpolation of T(k) with torch.searchsorted
+    lk = torch.log(K)
+    lkt = torch.as_tensor(np.log(kt), device=dev, dtype=torch.float64)
+    Ttt = torch.as_tensor(Tt, device=dev, dtype=torch.float64)
+    idx = torch.searchsorted(lkt, lk.reshape(-1)).clamp(1, lkt.numel() - 1).reshape(lk.shape)
+    w = (lk - lkt[idx - 1]) / (lkt[idx] - lkt[idx - 1])
+    T = Ttt[idx - 1] * (1 - w) + Ttt[idx] * w
+    P = torch.where(K2 > 0, K ** c["ns"] * T ** 2, torch.zeros_like(K2))
+    kk = np.logspace(np.log10(kt[0]), np.log10(kt[-1]), 4000)
+    Tk = np.interp(np.log(kk), np.log(kt), Tt)
+    x = kk * 8.0
+    W = 3.0 * (np.sin(x) - x * np.cos(x)) / x ** 3
+    s2 = np.trapezoid(kk ** (2 + c["ns"]) * Tk ** 2 * W ** 2 / (2.0 * np.pi ** 2), kk)
+    A = c["sigma8"] ** 2 / s2
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    white = torch.randn((ns, ns, ns), generator=gen, device=dev, dtype=torch.float64)
+    dk = torch.fft.rfftn(white) * torch.sqrt(A * P * float(ns) ** 3 / L ** 3)
+    del white
+    om = c["omega_dm"] + c["omega_b"]
+    D = _growth(1.0 / (1.0 + z), om, 1.0 - om) * growth_boost
+    invk2 = torch.where(K2 > 0, 1.0 / K2.clamp_min(1e-300), torch.zeros_like(K2))
+    g = torch.arange(ns, device=dev, dtype=torch.float64) + 0.5
+    pos = []
+    for ax, Kc in enumerate((KX, KY, KZ)):
+        psi = torch.fft.irfftn(1j * Kc * dk * invk2, s=(ns, ns, ns))
+        shape = [1, 1, 1]
+        shape[ax] = ns
+        pos.append(torch.remainder(g.reshape(shape) + D * psi / c["spacing"], ns).reshape(-1))
+    pos = torch.stack(pos, dim=1)
+    if ghost > 0:
+        out = []
+        for sx in (-1, 0, 1):
+            for sy in (-1, 0, 1):
+                for sz in (-1, 0, 1):
+                    q = pos + torch.tensor([sx, sy, sz], device=dev, dtype=torch.float64) * ns
+                    m = ((q >= -ghost) & (q < ns + ghost)).all(dim=1)
+                    out.append(q[m])
+        pos = torch.cat(out, dim=0) + ghost
+    hi = np.nextafter(np.float32(ns + 2 * ghost), np.float32(0))
+    pos = pos.to(torch.float32).clamp_max(float(hi)).cpu().numpy()
+    return _pack(pos[:, 0], pos[:, 1], pos[:, 2])
+
+
+def cutout(p, lo, hi):
+    """Particles of snapshot p inside the cube [lo, hi)^3, shifted to start at 0 (a bounded sample of the
+    same workload for the CPU baseline)."""
+    m = np.ones(p["x"].size, dtype=bool)
+    for k in ("x", "y", "z"):
+        m &= (p[k] >= lo) & (p[k] < hi)
+    q = {k: np.ascontiguousarray(v[m]) for k, v in p.items()}
+    for k in ("x", "y", "z"):
+        q[k] = (q[k] - np.float32(lo)).astype(np.float32)
+    q["id"] = np.arange(q["x"].size, dtype=np.int64)
+    return q

@@ -295,7 +295,8 @@ static void orc_collect_leaves(const orc_tree *t, const float *flo, const float 
 
 /* kernel_form: 0 generic nbody1 (RCBForceTree.cxx:604-618), 1 BG/Q scalar tail (BGQStep16.c:170-187 +
  * RCBForceTree.cxx:594-596), 2 = form 1 evaluated and accumulated in double (the "FP64 sum of the same
- * pair set" used to put both implementations' rounding errors on one scale). */
+ * pair set" used to put both implementations' rounding errors on one scale), 3 = like 2 but returns in vx
+ * the gross sum  sum_j |f_ij||d_ij|  (vy = vz = 0): the magnitude FP32 summation error scales with. */
 orc_result *orc_run(int64_t n, const float *x, const float *y, const float *z, const float *mass,
                     float *vx, float *vy, float *vz, /* in tree order on return: v += kick */
                     const float *boxes /* treeLo treeHi forceLo forceHi */, int law_kind, const float *coef,
@@ -397,7 +398,7 @@ orc_result *orc_run(int64_t n, const float *x, const float *y, const float *z, c
             }
             vx[off + i] = vx[off + i] + ax * fcoeff; vy[off + i] = vy[off + i] + ay * fcoeff; vz[off + i] = vz[off + i] + az * fcoeff;
           } else {
-            double ax = 0, ay = 0, az = 0;
+            double ax = 0, ay = 0, az = 0, gross = 0;
             for (int64_t j = 0; j < size; ++j) {
               double dx = (double)nx[j] - xi, dy = (double)ny[j] - yi, dz = (double)nz[j] - zi;
               double r2 = dx*dx + dy*dy + dz*dz;
@@ -408,10 +409,15 @@ orc_result *orc_run(int64_t n, const float *x, const float *y, const float *z, c
               double poly = 0; for (int k = 6; k >= 0; --k) poly = poly * r2 + (double)L.a[k];
               double f = (double)mi * nm[j] * (pow(r2 + (double)L.rsm2, -1.5) - poly);
               ax += f * dx; ay += f * dy; az += f * dz;
+              gross += fabs(f) * sqrt(r2);
               pc++;
             }
-            vx[off + i] = (float)(vx[off + i] + ax * fcoeff); vy[off + i] = (float)(vy[off + i] + ay * fcoeff);
-            vz[off + i] = (float)(vz[off + i] + az * fcoeff);
+            if (kernel_form == 3) {   /* gross = sum_j |f_ij| |d_ij|: the scale FP32 rounding error is relative to */
+              vx[off + i] = (float)(gross * fabs((double)fcoeff)); vy[off + i] = 0.0f; vz[off + i] = 0.0f;
+            } else {
+              vx[off + i] = (float)(vx[off + i] + ax * fcoeff); vy[off + i] = (float)(vy[off + i] + ay * fcoeff);
+              vz[off + i] = (float)(vz[off + i] + az * fcoeff);
+            }
           }
         }
       }
@@ -475,6 +481,16 @@ void orc_get_lists(const orc_result *R, int64_t *sink_leaf, int64_t *list_off, i
   memcpy(list_off, R->list_off, (size_t)(R->nsink + 1) * 8);
   memcpy(list_node, R->list_node, (size_t)R->list_off[R->nsink] * 8);
   memcpy(list_pseudo, R->list_pseudo, (size_t)R->list_off[R->nsink]);
+}
+
+/* f_over_r of the restated force law at n values of r2 (for force-law parity tests). */
+void orc_force_law_eval(int law_kind, const float *coef, int ncoef, float rsm, float rmax, int64_t n,
+                        const float *r2, float *out) {
+  orc_law L; memset(&L, 0, sizeof(L));
+  L.kind = law_kind;
+  for (int i = 0; i < 7; ++i) L.a[i] = (coef && i < ncoef) ? coef[i] : 0.0f;
+  L.rsm2 = rsm * rsm; L.r2min = 0.0f; L.r2max = rmax * rmax;
+  for (int64_t i = 0; i < n; ++i) out[i] = orc_f_over_r(&L, r2[i]);
 }
 
 void orc_free(orc_result *R) {

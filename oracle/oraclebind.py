@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 LAW_POLY, LAW_NEWTON = 0, 3
-FORM_GENERIC, FORM_BGQ_TAIL, FORM_FP64 = 0, 1, 2
+FORM_GENERIC, FORM_BGQ_TAIL, FORM_FP64, FORM_GROSS = 0, 1, 2, 3
 POLY5 = np.array([0.269327, -0.0750978, 0.0114808, -0.00109313, 0.0000605491, -0.00000147177],
                  dtype=np.float32)   # reference ForceLaw.cxx:109-114 == BGQStep16.c:167
 POLY6 = np.array([0.271431, -0.0783394, 0.0133122, -0.00159485, 0.000132336, -0.00000663394,
@@ -53,6 +53,7 @@ def _lib():
         dp = C.POINTER(C.c_double)
         lib.orc_direct_sum.argtypes = [C.c_int64, fp, fp, fp, fp, C.c_int64, ip, fp, C.c_int, C.c_float,
                                        C.c_float, dp, dp, dp]
+        lib.orc_force_law_eval.argtypes = [C.c_int, fp, C.c_int, C.c_float, C.c_float, C.c_int64, fp, fp]
         _LIB = lib
     return _LIB
 
@@ -119,3 +120,11 @@ def direct_sum(p, sel, rsm, rmax=RMAX, coef=POLY5):
     lib.orc_direct_sum(x.size, _fp(x), _fp(y), _fp(z), _fp(m), sel.size, _ip(sel), _fp(coef), len(coef),
                        rsm, float(rmax), *(v.ctypes.data_as(dp) for v in a))
     return np.stack(a, axis=1)
+
+
+def force_law_eval(r2, rsm, rmax=RMAX, coef=POLY5, law=LAW_POLY):
+    r2 = np.ascontiguousarray(r2, dtype=np.float32)
+    out = np.empty_like(r2)
+    coef = np.ascontiguousarray(coef, dtype=np.float32)
+    _lib().orc_force_law_eval(law, _fp(coef), len(coef), rsm, float(rmax), r2.size, _fp(r2), _fp(out))
+    return out

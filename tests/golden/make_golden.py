@@ -1,0 +1,42 @@
+"""Generate tests/golden/ref_*.npz by running the COMPILED REFERENCE (oracle/_ref/libhaccref.so, built
+from /root/reference by oracle/build_ref.sh) on small seeded snapshots.
+
+Run in the build container:  python tests/golden/make_golden.py
+Each fixture stores the input particles, the call parameters, and the reference's outputs: kicked
+velocities ordered by particle id, the reference's tree census and its evaluated / in-cutoff pair counts
+(the latter from the counting ForceLaw wrapper in oracle/ref_harness.cxx).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from hacc_coral_b200 import synth          # noqa: E402
+from oracle import refbind as R            # noqa: E402
+
+CASES = {
+    # name: (particles, box side, ppn, theta, law, edge)
+    "lattice16_ppn64": (synth.jitter_lattice(16, seed=11), 16, 64, 0.5, R.LAW_POLY5, 3.2),
+    "lattice8_rootleaf": (synth.jitter_lattice(8, seed=12), 8, 512, 0.5, R.LAW_POLY5, 0.0),
+    "clustered6k_ppn32": (synth.clustered(6000, 24.0, seed=13, n_clumps=6), 24, 32, 0.5, R.LAW_POLY5, 3.2),
+    "clustered6k_ppn32_theta01": (synth.clustered(6000, 24.0, seed=13, n_clumps=6), 24, 32, 0.1, R.LAW_POLY5, 3.2),
+    "zeld24_ppn100_poly6": (synth.zeldovich(24, z=50.0, seed=14, ghost=0), 24, 100, 0.5, R.LAW_POLY6, 3.2),
+}
+
+for name, (p, n, ppn, theta, law, edge) in CASES.items():
+    lo, hi, flo, fhi = [0.0] * 3, [float(n)] * 3, [edge] * 3, [float(n) - edge] * 3
+    q, st, tree = R.rcb_kick(p, lo, hi, flo, fhi, 0.007, theta, ppn, fcoeff=1.0, law=law, count_pairs=True,
+                             keep_tree=True)
+    o = np.argsort(q["id"], kind="stable")
+    out = os.path.join(HERE, "ref_%s.npz" % name)
+    np.savez_compressed(out, x=p["x"], y=p["y"], z=p["z"], n=n, ppn=ppn, theta=np.float32(theta), law=law,
+                        edge=np.float32(edge), rsm=np.float32(0.007),
+                        vx=q["vx"][o], vy=q["vy"][o], vz=q["vz"][o],
+                        nodes=st["nodes"], leaves=st["leaves"], empty_leaves=st["empty_leaves"],
+                        max_ppn=st["max_ppn"], mean_ppn=st["mean_ppn"], pairs_eval=st["pairs_eval"],
+                        pairs_incut=st["pairs_incut"],
+                        leaf_offset=tree["offset"][(tree["cl"] == 0) & (tree["cr"] == 0) & (tree["count"] > 0)],
+                        leaf_count=tree["count"][(tree["cl"] == 0) & (tree["cr"] == 0) & (tree["count"] > 0)])
+    print(name, p["x"].size, {k: st[k] for k in ("nodes", "leaves", "pairs_eval", "pairs_incut")}, os.path.getsize(out))

@@ -1,0 +1,74 @@
+"""CPU tests of the drop-in boundary: libhaccsr.so loads, exports every symbol include/haccsr.h declares,
+and refuses loudly (no CPU fallback) when no B200 is visible."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import hacc_coral_b200 as H
+from hacc_coral_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "haccsr.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(haccsr_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_is_built_in_tree():
+    H.build()
+    assert os.path.exists(H.lib_path())
+    assert os.path.dirname(H.lib_path()).endswith(os.path.join("hacc_coral_b200", "csrc"))
+
+
+def test_exports_every_declared_symbol():
+    H.build()
+    lib = ctypes.CDLL(H.lib_path())
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "libhaccsr.so does not export %s" % n
+    assert sorted(capi.EXPORTS) == names
+
+
+def test_stats_struct_layout_matches_header():
+    src = open(os.path.join(ROOT, "include", "haccsr.h")).read()
+    body = re.search(r"typedef struct haccsr_stats \{(.*?)\} haccsr_stats;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(?:int64_t|uint64_t|double|float|int32_t)\s+([a-z_]+);", body)
+    assert fields == [f for f, _ in capi.KickStats._fields_]
+
+
+def test_sass_is_blackwell_native():
+    """The force kernel must contain TMA bulk copies (UBLKCP) and MUFU.RSQ; built for sm_100a only."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    H.build()
+    elf = subprocess.run(["cuobjdump", "-lelf", H.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run(["cuobjdump", "-sass", H.lib_path()], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "MUFU.RSQ" in sass and "SYNCS" in sass
+
+
+def test_fails_loudly_without_gpu():
+    lib = H.load_library()
+    if lib.haccsr_device_count() > 0:
+        pytest.skip("a B200 is visible")
+    with pytest.raises(H.HaccSRError) as e:
+        H.HaccSR(1000)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through oracle/ (test infrastructure only)."""
+    pkg = os.path.join(ROOT, "hacc_coral_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cxx", ".cpp")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oraclebind" not in txt and "refbind" not in txt and "liboracle" not in txt, f

@@ -26,6 +26,12 @@ def run(name, p, n, ppn, theta, law_coef=H.POLY5):
     t2 = time.time()
     cmp_ = compare_trees(tr, out["id"], o["tree"], o["id"])
     rel, d, nb, rms = accel_errors(by_id(out), by_id(o))
+    if p["x"].size <= 400000:
+        o64 = O.run(p, lo, hi, flo, fhi, RSM, theta, ppn, coef=law_coef, form=O.FORM_FP64)
+        r1, _, _, _ = accel_errors(by_id(out), by_id(o64))
+        r2, _, _, _ = accel_errors(by_id(o), by_id(o64))
+        print("   vs FP64 same-pair-set sum: gpu max %.3e p99.9 %.3e median %.3e | cpu-ref max %.3e p99.9 %.3e median %.3e" % (
+            r1.max(), np.quantile(r1, 0.999), np.median(r1), r2.max(), np.quantile(r2, 0.999), np.median(r2)))
     os_ = o["stats"]
     print("== %s n=%d N=%d ppn=%d theta=%.2f  oracle %.1fs gpu-call %.2fs" % (name, n, p["x"].size, ppn, theta, t1 - t0, t2 - t1))
     print("   tree:", cmp_)
