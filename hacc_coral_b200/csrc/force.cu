@@ -26,7 +26,7 @@
 
 namespace haccsr {
 
-static constexpr int SMAX_ = 8;        // max sinks per thread
+static constexpr int SMAX_ = 6;        // max sinks per thread (3 packed pairs): 6 x 32 = 192 sinks per work item
 static constexpr int FTILE = 128;      // sources per shared-memory tile
 static constexpr int FSTAGES = 4;      // ring depth
 
@@ -70,31 +70,65 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
   return y;
 }
 
-// One source applied to S sinks.  LAW: 0 = SR-poly with NC coefficients, 1 = Newton.
-template <int S, int NC, int LAW, bool GUARD0, bool COUNT>
-__device__ __forceinline__ void interact(const float4 s, const float (&xi)[S], const float (&yi)[S],
-                                         const float (&zi)[S], float (&ax)[S], float (&ay)[S], float (&az)[S],
-                                         const ForceParams &P, unsigned (&cnt)[S]) {
+// ---- the pair arithmetic ---------------------------------------------------------------------------------
+// Packed FP32x2 (FFMA2 / FADD2 / FMUL2, new on sm_100): one instruction works on the pairs (source j, sink a)
+// and (source j, sink b); the source coordinate is the instruction's broadcast scalar operand, the two sinks
+// sit in an aligned register pair.  This halves the issue slots of the FMA-pipe work, which moves the bound
+// from the issue port (25.4 instructions per pair in the scalar form, profiles/r1_force_ncu_summary.md) to the
+// FMA pipe itself (21 lane-operations per pair).
+// Rounding: every operation is round-to-nearest on each half, the same sequence as the scalar form, so a sink
+// gets bit-identical results whether it is processed in a packed pair or in the scalar remainder group.
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it never does for the scalar .rn forms), so
+// the three squares of r2 are formed with scalar mul.rn and only summed packed: r2 keeps the reference's
+// unfused value (dx*dx + dy*dy) + dz*dz and the set of pairs inside the cutoff stays bit-identical to the CPU's.
+struct SinkRegs2 { float2 nx, ny, nz, ax, ay, az; };   // two sinks: negated position, accumulators
+struct SinkRegs1 { float nx, ny, nz, ax, ay, az; };
+
+template <int NC, int LAW, bool GUARD0, bool COUNT>
+__device__ __forceinline__ void interact2(const float4 s, SinkRegs2 &k, const ForceParams &P, unsigned &cnt_a, unsigned &cnt_b) {
+  const float2 dx = __fadd2_rn(make_float2(s.x, s.x), k.nx), dy = __fadd2_rn(make_float2(s.y, s.y), k.ny),
+               dz = __fadd2_rn(make_float2(s.z, s.z), k.nz);
+  // reference order, no contraction: (dx*dx + dy*dy) + dz*dz   (RCBForceTree.cxx:608, BGQStep16.c:176)
+  const float2 qx = make_float2(__fmul_rn(dx.x, dx.x), __fmul_rn(dx.y, dx.y));
+  const float2 qy = make_float2(__fmul_rn(dy.x, dy.x), __fmul_rn(dy.y, dy.y));
+  const float2 qz = make_float2(__fmul_rn(dz.x, dz.x), __fmul_rn(dz.y, dz.y));
+  const float2 r2 = __fadd2_rn(__fadd2_rn(qx, qy), qz);
+  const float2 t = __fadd2_rn(r2, make_float2(P.rsm2, P.rsm2));
+  const float2 t3 = __fmul2_rn(__fmul2_rn(t, t), t);
+  float2 f = make_float2(rsqrt_ftz(t3.x), rsqrt_ftz(t3.y));
+  if (LAW == 0) {
+    float2 p = make_float2(P.a[NC - 1], P.a[NC - 1]);
 #pragma unroll
-  for (int k = 0; k < S; ++k) {
-    float dx = __fsub_rn(s.x, xi[k]), dy = __fsub_rn(s.y, yi[k]), dz = __fsub_rn(s.z, zi[k]);
-    // reference order, no contraction: (dx*dx + dy*dy) + dz*dz   (RCBForceTree.cxx:608, BGQStep16.c:176)
-    float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-    float t = r2 + P.rsm2;
-    float f = rsqrt_ftz(t * t * t);
-    if (LAW == 0) {
-      float p = P.a[NC - 1];
-#pragma unroll
-      for (int q = NC - 2; q >= 0; --q) p = fmaf(p, r2, P.a[q]);
-      f -= p;
-    }
-    f *= s.w;
-    bool in = r2 < P.rmax2;
-    if (GUARD0) in = in && (r2 > 0.0f);
-    f = in ? f : 0.0f;
-    if (COUNT) cnt[k] += (in && r2 > 0.0f) ? 1u : 0u;
-    ax[k] = fmaf(f, dx, ax[k]); ay[k] = fmaf(f, dy, ay[k]); az[k] = fmaf(f, dz, az[k]);
+    for (int q = NC - 2; q >= 0; --q) p = __ffma2_rn(p, r2, make_float2(P.a[q], P.a[q]));
+    f = __fadd2_rn(f, make_float2(-p.x, -p.y));
   }
+  f = __fmul2_rn(f, make_float2(s.w, s.w));
+  bool in_a = r2.x < P.rmax2, in_b = r2.y < P.rmax2;
+  if (GUARD0) { in_a = in_a && (r2.x > 0.0f); in_b = in_b && (r2.y > 0.0f); }
+  f.x = in_a ? f.x : 0.0f;
+  f.y = in_b ? f.y : 0.0f;
+  if (COUNT) { cnt_a += (in_a && r2.x > 0.0f) ? 1u : 0u; cnt_b += (in_b && r2.y > 0.0f) ? 1u : 0u; }
+  k.ax = __ffma2_rn(f, dx, k.ax); k.ay = __ffma2_rn(f, dy, k.ay); k.az = __ffma2_rn(f, dz, k.az);
+}
+
+template <int NC, int LAW, bool GUARD0, bool COUNT>
+__device__ __forceinline__ void interact1(const float4 s, SinkRegs1 &k, const ForceParams &P, unsigned &cnt) {
+  const float dx = __fadd_rn(s.x, k.nx), dy = __fadd_rn(s.y, k.ny), dz = __fadd_rn(s.z, k.nz);
+  const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  const float t = __fadd_rn(r2, P.rsm2);
+  float f = rsqrt_ftz(__fmul_rn(__fmul_rn(t, t), t));
+  if (LAW == 0) {
+    float p = P.a[NC - 1];
+#pragma unroll
+    for (int q = NC - 2; q >= 0; --q) p = __fmaf_rn(p, r2, P.a[q]);
+    f = __fadd_rn(f, -p);
+  }
+  f = __fmul_rn(f, s.w);
+  bool in = r2 < P.rmax2;
+  if (GUARD0) in = in && (r2 > 0.0f);
+  f = in ? f : 0.0f;
+  if (COUNT) cnt += (in && r2 > 0.0f) ? 1u : 0u;
+  k.ax = __fmaf_rn(f, dx, k.ax); k.ay = __fmaf_rn(f, dy, k.ay); k.az = __fmaf_rn(f, dz, k.az);
 }
 
 struct Producer {
@@ -104,8 +138,9 @@ struct Producer {
   unsigned remaining;     // sources still to be fetched
 };
 
-// lane 0 only: post the copies of the next tile into `stage`
-__device__ __forceinline__ void produce_tile(Producer &pr, const ForceParams &P, float4 *tile, unsigned bar) {
+// lane 0 only: post the copies of the next tile into `stage`.  Deliberately not inlined: one copy of this
+// cold code instead of five per (S2, ODD) variant keeps the kernel's instruction footprint small.
+__device__ __noinline__ void produce_tile(Producer &pr, const ForceParams &P, float4 *tile, unsigned bar) {
   unsigned n = pr.remaining < (unsigned)FTILE ? pr.remaining : (unsigned)FTILE;
   if (n == 0) return;
   mbar_expect_tx(bar, n * 16u);
@@ -122,20 +157,36 @@ __device__ __forceinline__ void produce_tile(Producer &pr, const ForceParams &P,
   pr.remaining -= n;
 }
 
-template <int S, int NC, int LAW, bool GUARD0, bool COUNT>
+// One work item: S = 2*S2 + ODD groups of 32 sinks (group g = sinks g*32 + lane of the chunk); groups 2k, 2k+1
+// form packed pair k, an odd last group runs the scalar form.  Loop bodies are kept small on purpose (at most
+// ~130 instructions): the eight (S2, ODD) variants together fit the 32 KB instruction cache, which the first
+// version's 4x-unrolled bodies (72 KB) did not -- that showed as "no_instruction" stalls, worst on clustered
+// snapshots where all eight variants are in flight on one SM.
+template <int S2, bool ODD, int NC, int LAW, bool GUARD0, bool COUNT>
 __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P, float4 (*tiles)[FTILE],
                                          unsigned long long *bars) {
+  constexpr int S = 2 * S2 + (ODD ? 1 : 0);
+  constexpr int UNR = (S <= 2) ? 4 : ((S <= 4) ? 2 : 1);
   const int lane = threadIdx.x;
-  float xi[S], yi[S], zi[S], mi[S], ax[S], ay[S], az[S];
+  SinkRegs2 k2[S2 > 0 ? S2 : 1];
+  SinkRegs1 k1;
   const int node_off_sink = it.sink_begin;
 #pragma unroll
-  for (int k = 0; k < S; ++k) {
-    int j = k * 32 + lane;
+  for (int g = 0; g < S; ++g) {
+    int j = g * 32 + lane;
     // lanes past the end of the chunk re-use the chunk's first sink (finite numbers, result discarded)
     float4 s = __ldg(P.src4 + node_off_sink + (j < it.sink_count ? j : 0));
-    xi[k] = s.x; yi[k] = s.y; zi[k] = s.z; mi[k] = s.w;
-    ax[k] = ay[k] = az[k] = 0.f;
+    if (g < 2 * S2) {
+      SinkRegs2 &k = k2[g >> 1];
+      if ((g & 1) == 0) { k.nx.x = -s.x; k.ny.x = -s.y; k.nz.x = -s.z; }
+      else { k.nx.y = -s.x; k.ny.y = -s.y; k.nz.y = -s.z; }
+    } else {
+      k1.nx = -s.x; k1.ny = -s.y; k1.nz = -s.z;
+    }
   }
+#pragma unroll
+  for (int k = 0; k < S2; ++k) k2[k].ax = k2[k].ay = k2[k].az = make_float2(0.f, 0.f);
+  k1.ax = k1.ay = k1.az = 0.f;
   Producer pr;
   pr.ranges = P.ranges; pr.ri = P.range_off[it.node]; pr.rend = P.range_off[it.node + 1];
   pr.roff = 0; pr.remaining = P.list_len[it.node];
@@ -147,36 +198,42 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
   }
   unsigned cnt[S];
 #pragma unroll
-  for (int k = 0; k < S; ++k) cnt[k] = 0;
+  for (int g = 0; g < S; ++g) cnt[g] = 0;
   for (unsigned t = 0; t < ntiles; ++t) {
     const int stage = t % FSTAGES;
     const unsigned parity = (t / FSTAGES) & 1u;
     mbar_wait(smem_u32(&bars[stage]), parity);
     const unsigned nsrc = (t + 1 == ntiles) ? (total - t * FTILE) : (unsigned)FTILE;
     const float4 *tile = tiles[stage];
-    unsigned j = 0;
-    for (; j + 4 <= nsrc; j += 4) {
+#pragma unroll UNR
+    for (unsigned j = 0; j < nsrc; ++j) {
+      const float4 s = tile[j];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) interact<S, NC, LAW, GUARD0, COUNT>(tile[j + u], xi, yi, zi, ax, ay, az, P, cnt);
+      for (int k = 0; k < S2; ++k) interact2<NC, LAW, GUARD0, COUNT>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
+      if (ODD) interact1<NC, LAW, GUARD0, COUNT>(s, k1, P, cnt[S - 1]);
     }
-    for (; j < nsrc; ++j) interact<S, NC, LAW, GUARD0, COUNT>(tile[j], xi, yi, zi, ax, ay, az, P, cnt);
     __syncwarp();                       // every lane is done reading this stage
     if (lane == 0) produce_tile(pr, P, tiles[stage], smem_u32(&bars[stage]));
   }
   // kick: v += fcoeff * m_i * a   (RCBForceTree.cxx:594-596 / :615-617)
 #pragma unroll
-  for (int k = 0; k < S; ++k) {
-    int j = k * 32 + lane;
+  for (int g = 0; g < S; ++g) {
+    int j = g * 32 + lane;
     if (j < it.sink_count) {
-      int g = node_off_sink + j;
-      float c = P.fcoeff * mi[k];
-      P.vx[g] = fmaf(c, ax[k], P.vx[g]); P.vy[g] = fmaf(c, ay[k], P.vy[g]); P.vz[g] = fmaf(c, az[k], P.vz[g]);
+      float ax, ay, az;
+      if (g < 2 * S2) {
+        const SinkRegs2 &k = k2[g >> 1];
+        ax = (g & 1) ? k.ax.y : k.ax.x; ay = (g & 1) ? k.ay.y : k.ay.x; az = (g & 1) ? k.az.y : k.az.x;
+      } else { ax = k1.ax; ay = k1.ay; az = k1.az; }
+      int gi = node_off_sink + j;
+      float c = P.fcoeff * __ldg(&P.src4[gi].w);
+      P.vx[gi] = fmaf(c, ax, P.vx[gi]); P.vy[gi] = fmaf(c, ay, P.vy[gi]); P.vz[gi] = fmaf(c, az, P.vz[gi]);
     }
   }
   if (COUNT) {
     unsigned long long c64 = 0;   // padded lanes duplicate the chunk's first sink: not counted
 #pragma unroll
-    for (int k = 0; k < S; ++k) c64 += (k * 32 + lane < it.sink_count) ? cnt[k] : 0u;
+    for (int g = 0; g < S; ++g) c64 += (g * 32 + lane < it.sink_count) ? cnt[g] : 0u;
     for (int o = 16; o > 0; o >>= 1) c64 += __shfl_down_sync(0xffffffffu, c64, o);
     if (lane == 0) atomicAdd(P.incut, c64);
   }
@@ -197,14 +254,12 @@ __global__ void __launch_bounds__(32) k_force(const __grid_constant__ ForceParam
   const WorkItem it = P.items[item];
   const int S = (it.sink_count + 31) / 32;
   switch (S) {
-    case 1: run_item<1, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    case 2: run_item<2, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    case 3: run_item<3, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    case 4: run_item<4, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    case 5: run_item<5, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    case 6: run_item<6, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    case 7: run_item<7, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    default: run_item<8, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    case 1: run_item<0, true, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    case 2: run_item<1, false, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    case 3: run_item<1, true, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    case 4: run_item<2, false, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    case 5: run_item<2, true, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+    default: run_item<3, false, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
   }
 }
 

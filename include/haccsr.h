@@ -37,6 +37,12 @@ enum {
   /* ForceLawSR over a polynomial grid force: f(r2) = (r2+rsm^2)^-3/2 - sum_k a[k] r2^k, for r2 < rmax^2
    * (ForceLaw.cxx:137-141,187-192; BGQStep16.c:167-187).  ncoef <= 7. */
   HACCSR_LAW_SR_POLY = 0,
+  /* ForceLawSR over the analytic grid-force fit FGridEvalFit (ForceLaw.cxx:39-51,70-80): coeffs = the eight
+   * constants b c d e f g h l of FGrid (ForceLaw.cxx:23-31), ncoef = 8.  The default of run_hacc.sh (no -P). */
+  HACCSR_LAW_SR_FIT = 1,
+  /* ForceLawSR over FGridEvalInterp (ForceLaw.cxx:145-172): coeffs = the grid force tabulated at
+   * r2 = i * rmax^2 / (ncoef - 1), i = 0 .. ncoef-1 (2 <= ncoef <= 4096), linear interpolation in r2. */
+  HACCSR_LAW_SR_INTERP = 2,
   /* ForceLawNewton: f(r2) = r2^-3/2 (ForceLaw.h:102-107), used when the caller passes fl == NULL
    * (RCBForceTree.cxx:395-404); pairs with r2 == 0 contribute nothing (the guard of BGQStep16.c:183). */
   HACCSR_LAW_NEWTON = 3

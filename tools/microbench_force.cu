@@ -62,9 +62,14 @@ __global__ void __launch_bounds__(32) k_scalar(const float4 *__restrict__ src, f
 }
 
 // ---- V2: packed f32x2, two SINKS per instruction; the source is duplicated into register pairs --------
-template <int S2, bool EXACT>   // S2 = sink pairs per thread
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it does not for the scalar forms), so the
+// unfused sum of squares needs an operand ptxas cannot see through: XOR with a run-time zero (ALU pipe).
+__device__ __forceinline__ float2 opaque2(float2 v, unsigned zero) {
+  return make_float2(__uint_as_float(__float_as_uint(v.x) ^ zero), __uint_as_float(__float_as_uint(v.y) ^ zero));
+}
+template <int S2, int EXACT>   // S2 = sink pairs per thread
 __device__ __forceinline__ void pair_sink2(const float4 s, const float2 (&xi)[S2], const float2 (&yi)[S2], const float2 (&zi)[S2],
-                                           float2 (&ax)[S2], float2 (&ay)[S2], float2 (&az)[S2], const Law &L) {
+                                           float2 (&ax)[S2], float2 (&ay)[S2], float2 (&az)[S2], const Law &L, unsigned zero) {
   const float2 sx = make_float2(s.x, s.x), sy = make_float2(s.y, s.y), sz = make_float2(s.z, s.z), sw = make_float2(s.w, s.w);
   const float2 rsm2 = make_float2(L.rsm2, L.rsm2);
 #pragma unroll
@@ -72,7 +77,13 @@ __device__ __forceinline__ void pair_sink2(const float4 s, const float2 (&xi)[S2
     // d = s - xi  as  s + (-xi): the sinks are stored negated
     float2 dx = __fadd2_rn(sx, xi[k]), dy = __fadd2_rn(sy, yi[k]), dz = __fadd2_rn(sz, zi[k]);
     float2 r2;
-    if (EXACT) r2 = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
+    if (EXACT == 3) {   // squares as scalar mul.rn (never contracted by ptxas), sums packed
+      float2 qx = make_float2(__fmul_rn(dx.x, dx.x), __fmul_rn(dx.y, dx.y));
+      float2 qy = make_float2(__fmul_rn(dy.x, dy.x), __fmul_rn(dy.y, dy.y));
+      float2 qz = make_float2(__fmul_rn(dz.x, dz.x), __fmul_rn(dz.y, dz.y));
+      r2 = __fadd2_rn(__fadd2_rn(qx, qy), qz);
+    } else if (EXACT == 2) r2 = __fadd2_rn(__fadd2_rn(opaque2(__fmul2_rn(dx, dx), zero), opaque2(__fmul2_rn(dy, dy), zero)), opaque2(__fmul2_rn(dz, dz), zero));
+    else if (EXACT == 1) r2 = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
     else r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
     float2 t = __fadd2_rn(r2, rsm2);
     float2 t3 = __fmul2_rn(__fmul2_rn(t, t), t);
@@ -88,8 +99,8 @@ __device__ __forceinline__ void pair_sink2(const float4 s, const float2 (&xi)[S2
   }
 }
 
-template <int S2, bool EXACT>
-__global__ void __launch_bounds__(32) k_sink2(const float4 *__restrict__ src, float4 *__restrict__ out, Law L, int nrep) {
+template <int S2, int EXACT, int UNROLL>
+__global__ void __launch_bounds__(32) k_sink2(const float4 *__restrict__ src, float4 *__restrict__ out, Law L, int nrep, unsigned zero) {
   __shared__ float4 tile[TILE];
   for (int i = threadIdx.x; i < TILE; i += 32) tile[i] = src[(blockIdx.x * TILE + i) & 0xffff];
   __syncwarp();
@@ -102,8 +113,8 @@ __global__ void __launch_bounds__(32) k_sink2(const float4 *__restrict__ src, fl
     ax[k] = ay[k] = az[k] = make_float2(0.f, 0.f);
   }
   for (int r = 0; r < nrep; ++r) {
-#pragma unroll 4
-    for (int j = 0; j < TILE; ++j) pair_sink2<S2, EXACT>(tile[j], xi, yi, zi, ax, ay, az, L);
+#pragma unroll UNROLL
+    for (int j = 0; j < TILE; ++j) pair_sink2<S2, EXACT>(tile[j], xi, yi, zi, ax, ay, az, L, zero);
   }
   float sx = 0, sy = 0, sz = 0;
 #pragma unroll
@@ -205,10 +216,13 @@ int main(int argc, char **argv) {
   Law L = {{0.269327f, -0.0750978f, 0.0114808f, -0.00109313f, 0.0000605491f, -0.00000147177f}, 0.007f * 0.007f, 3.116326355f * 3.116326355f};
   const int nrep = 200;
 #define RUN_SCALAR(S, E) run("scalar " #E, [&](int g, int n) { k_scalar<S, E><<<g, 32>>>(src, out, L, n); }, S, grid, nrep, peak)
-#define RUN_SINK2(S2, E) run("sink-packed " #E, [&](int g, int n) { k_sink2<S2, E><<<g, 32>>>(src, out, L, n); }, 2 * S2, grid, nrep, peak)
+#define RUN_SINK2(S2, E, U) run("sink-packed mode" #E " unroll" #U, [&](int g, int n) { k_sink2<S2, E, U><<<g, 32>>>(src, out, L, n, zero); }, 2 * S2, grid, nrep, peak)
 #define RUN_SRC2(S, E) run("source-packed " #E, [&](int g, int n) { k_src2<S, E><<<g, 32>>>(src, out, L, n); }, S, grid, nrep, peak)
   RUN_SCALAR(4, true); RUN_SCALAR(8, true); RUN_SCALAR(4, false); RUN_SCALAR(8, false);
-  RUN_SINK2(2, true); RUN_SINK2(4, true); RUN_SINK2(6, true); RUN_SINK2(2, false); RUN_SINK2(4, false); RUN_SINK2(6, false);
+  const unsigned zero = (argc > 5) ? 1u : 0u;
+  RUN_SINK2(1, 2, 4); RUN_SINK2(2, 2, 4); RUN_SINK2(3, 2, 2); RUN_SINK2(4, 2, 1); RUN_SINK2(4, 2, 2); RUN_SINK2(4, 2, 4); RUN_SINK2(6, 2, 1);
+  RUN_SINK2(1, 3, 4); RUN_SINK2(2, 3, 4); RUN_SINK2(3, 3, 2); RUN_SINK2(4, 3, 1); RUN_SINK2(4, 3, 2); RUN_SINK2(4, 3, 4); RUN_SINK2(6, 3, 1);
+  RUN_SINK2(1, 0, 4); RUN_SINK2(2, 0, 4); RUN_SINK2(3, 0, 2); RUN_SINK2(4, 0, 1); RUN_SINK2(4, 0, 2); RUN_SINK2(4, 0, 4); RUN_SINK2(6, 0, 1);
   RUN_SRC2(2, true); RUN_SRC2(4, true); RUN_SRC2(6, true); RUN_SRC2(8, true); RUN_SRC2(4, false); RUN_SRC2(8, false);
   return 0;
 }
