@@ -43,4 +43,12 @@ def build(force=False, verbose=False):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", HOST,
                                    "-I", os.path.join(_HERE, "..", "include"), "-o", fout, facade_src,
                                    "-L", CSRC, "-lhaccsr", "-Wl,-rpath,$ORIGIN/../csrc"])
+    test_src = os.path.join(_HERE, "..", "tests", "cxx", "facade_test.cxx")
+    fout = os.path.join(HOST, "libhaccsr_facade.so")
+    if os.path.exists(test_src) and os.path.exists(fout):
+        texe = os.path.join(_HERE, "..", "tests", "cxx", "facade_test")
+        if force or _stale(texe, [test_src, fout]):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", HOST, "-I", os.path.join(_HERE, "..", "include"),
+                                   "-o", texe, test_src, "-L", HOST, "-lhaccsr_facade", "-L", CSRC, "-lhaccsr",
+                                   "-Wl,-rpath,$ORIGIN/../../hacc_coral_b200/host:$ORIGIN/../../hacc_coral_b200/csrc"])
     return out

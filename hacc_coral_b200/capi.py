@@ -7,7 +7,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-LAW_SR_POLY, LAW_NEWTON = 0, 3
+LAW_SR_POLY, LAW_SR_FIT, LAW_SR_INTERP, LAW_NEWTON = 0, 1, 2, 3
 # reference src/halo_finder/ForceLaw.cxx:109-114 (== BGQStep16.c:167) and :98-104
 POLY5 = np.array([0.269327, -0.0750978, 0.0114808, -0.00109313, 0.0000605491, -0.00000147177], dtype=np.float32)
 POLY6 = np.array([0.271431, -0.0783394, 0.0133122, -0.00159485, 0.000132336, -0.00000663394, 0.000000147305],
@@ -70,6 +70,8 @@ def load_library():
     lib.haccsr_stream.argtypes = [vp, C.c_float]
     lib.haccsr_partition_in_box.argtypes = [vp, fp, ip64]
     lib.haccsr_fill_mass.argtypes = [vp, C.c_float]
+    lib.haccsr_subcycle.argtypes = [vp, C.c_int, C.c_float, fp, fp, fp, fp, fp, C.c_float, C.c_int64, C.c_int, C.c_float,
+                                    C.POINTER(KickStats)]
     i32p = C.POINTER(C.c_int32)
     lib.haccsr_get_tree.argtypes = [vp, C.c_int64, ip64, i32p, i32p, i32p, i32p, fp]
     u32p = C.POINTER(C.c_uint32)
@@ -81,7 +83,7 @@ def load_library():
 EXPORTS = ["haccsr_last_error", "haccsr_device_count", "haccsr_create", "haccsr_destroy", "haccsr_set_stream",
            "haccsr_set_force_law", "haccsr_upload", "haccsr_download", "haccsr_host_register",
            "haccsr_host_unregister", "haccsr_kick", "haccsr_stream", "haccsr_partition_in_box",
-           "haccsr_fill_mass", "haccsr_get_tree", "haccsr_get_lists"]
+           "haccsr_fill_mass", "haccsr_subcycle", "haccsr_get_tree", "haccsr_get_lists"]
 
 _F32 = ("x", "y", "z", "vx", "vy", "vz", "mass", "phi")
 
@@ -171,6 +173,13 @@ class HaccSR:
         nin = C.c_int64()
         self._check(self.lib.haccsr_partition_in_box(self._h, _f3(hi), C.byref(nin)))
         return nin.value
+
+    def subcycle(self, nsub, prefactor_tau, box_hi, tree_lo, tree_hi, force_lo, force_hi, theta, ppn, fcoeff, tdpts=1):
+        """Particles::subCycle on the resident particles; returns the summed stats."""
+        st = KickStats()
+        self._check(self.lib.haccsr_subcycle(self._h, int(nsub), prefactor_tau, _f3(box_hi), _f3(tree_lo), _f3(tree_hi),
+                                             _f3(force_lo), _f3(force_hi), theta, int(ppn), tdpts, fcoeff, C.byref(st)))
+        return st.as_dict()
 
     def tree(self):
         nn = C.c_int64()

@@ -153,7 +153,7 @@ int haccsr_destroy(haccsr_ctx *c) {
   c->nidA.release(); c->nidB.release(); c->nodes.release(); c->acc.release(); c->lstart.release(); c->lend.release();
   c->lbase.release(); c->nleft.release(); c->tilecount.release(); c->tilebase.release(); c->scratch_u32.release();
   c->n_ranges.release(); c->n_pseudo.release(); c->range_off.release(); c->pseudo_off.release(); c->list_len.release();
-  c->ranges.release(); c->pool.release(); c->item_cnt.release(); c->item_off.release(); c->items.release();
+  c->ranges.release(); c->pool.release(); c->law_table.release(); c->item_cnt.release(); c->item_off.release(); c->items.release(); c->items_sorted.release(); c->lpt_hist.release();
   if (c->h_level) cudaFreeHost(c->h_level);
   if (c->d_level) cudaFree(c->d_level);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -174,16 +174,38 @@ int haccsr_set_stream(haccsr_ctx *c, void *cuda_stream) {
 
 int haccsr_set_force_law(haccsr_ctx *c, int kind, const float *coeffs, int ncoef, float rsm, float rmax) {
   if (!c) { set_error("null context"); return 1; }
-  if (kind != HACCSR_LAW_SR_POLY && kind != HACCSR_LAW_NEWTON) {
-    set_error("unsupported force law kind %d (supported: SR_POLY=0, NEWTON=3); no CPU fallback", kind);
+  if (kind != HACCSR_LAW_SR_POLY && kind != HACCSR_LAW_NEWTON && kind != HACCSR_LAW_SR_FIT && kind != HACCSR_LAW_SR_INTERP) {
+    set_error("unsupported force law kind %d (supported: SR_POLY=0, SR_FIT=1, SR_INTERP=2, NEWTON=3); no CPU fallback", kind);
     return 1;
   }
   if (kind == HACCSR_LAW_SR_POLY && (ncoef < 1 || ncoef > 7 || !coeffs)) { set_error("SR_POLY needs 1..7 coefficients"); return 1; }
+  if (kind == HACCSR_LAW_SR_FIT && (ncoef != 8 || !coeffs)) { set_error("SR_FIT needs the 8 constants b c d e f g h l"); return 1; }
+  if (kind == HACCSR_LAW_SR_INTERP && (ncoef < 2 || ncoef > 4096 || !coeffs)) { set_error("SR_INTERP needs a table of 2..4096 samples"); return 1; }
   if (!(rmax > 0.f)) { set_error("rmax must be positive"); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
   memset(&c->law, 0, sizeof(c->law));
   c->law.kind = kind;
-  c->law.ncoef = (kind == HACCSR_LAW_SR_POLY) ? ncoef : 0;
+  c->law.ncoef = (kind == HACCSR_LAW_SR_POLY || kind == HACCSR_LAW_SR_FIT) ? ncoef : 0;
   for (int i = 0; i < c->law.ncoef; ++i) c->law.a[i] = coeffs[i];
+  if (kind == HACCSR_LAW_SR_INTERP) {
+    // the evaluator's constants exactly as FGridEvalInterp derives them (ForceLaw.cxx:54-65,145-152):
+    // r2_i = float(i * dr2) with dr2 = rmax^2 / (n - 1) in double; m_dr2, m_oodr2 in float
+    const int n = ncoef;
+    float *h = (float *)malloc(2 * (size_t)n * sizeof(float));
+    if (!h) { set_error("out of host memory"); return 2; }
+    const double dr2 = (double)(rmax * rmax) / (n - 1.0);
+    for (int i = 0; i < n; ++i) { h[i] = coeffs[i]; h[n + i] = (float)(i * dr2); }
+    c->law.ntab = n;
+    c->law.tab_r2min = h[n]; c->law.tab_r2max = h[2 * n - 1];
+    const float fdr2 = (float)((c->law.tab_r2max - c->law.tab_r2min) / (n - 1.0));
+    c->law.tab_oodr2 = (float)(1.0 / fdr2);
+    int rc = c->law_table.ensure(2 * (size_t)n);
+    if (rc == 0 && cudaMemcpy(c->law_table.p, h, 2 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("copy of the interpolation table failed"); rc = 2;
+    }
+    free(h);
+    if (rc) return rc;
+  }
   c->law.rsm2 = (kind == HACCSR_LAW_NEWTON) ? 0.0f : rsm * rsm;   // ForceLaw.cxx:177 (m_rsm2 = rsm*rsm, float)
   c->law.rmax = rmax;
   c->law.rmax2 = rmax * rmax;                                     // RCBForceTree.cxx:582 (float product)
@@ -309,6 +331,34 @@ int haccsr_partition_in_box(haccsr_ctx *c, const float hi[3], int64_t *count_in_
   HSR_CUDA(cudaGetLastError());
   Soa t = c->cur; c->cur = c->alt; c->alt = t;
   if (count_in_box) *count_in_box = nin;
+  return 0;
+}
+
+int haccsr_subcycle(haccsr_ctx *c, int nsub, float pt, const float box_hi[3], const float tree_lo[3], const float tree_hi[3],
+                    const float force_lo[3], const float force_hi[3], float theta, int64_t ppn, int tdpts, float fcoeff,
+                    haccsr_stats *stats) {
+  if (!c) { set_error("null context"); return 1; }
+  if (nsub < 1) { set_error("haccsr_subcycle: nsub must be >= 1"); return 1; }
+  if (!box_hi) { set_error("haccsr_subcycle: null box"); return 1; }
+  haccsr_stats sum; memset(&sum, 0, sizeof(sum));
+  for (int s = 0; s < nsub; ++s) {
+    haccsr_stats st;
+    int64_t nin = 0;
+    HSR_TRY(haccsr_stream(c, pt));                                  // Particles.cxx:1185-1186
+    HSR_TRY(haccsr_partition_in_box(c, box_hi, &nin));              // :1243-1248 (resortParticles, Np = m_Np_last)
+    HSR_TRY(haccsr_fill_mass(c, 1.0f));                             // :1256-1257
+    HSR_TRY(haccsr_kick(c, nin, tree_lo, tree_hi, force_lo, force_hi, theta, ppn, tdpts, fcoeff, nullptr, &st));
+    HSR_TRY(haccsr_stream(c, pt));                                  // :1194-1195
+    const uint64_t pairs = sum.pairs_evaluated + st.pairs_evaluated;
+    const float b = sum.ms_build + st.ms_build, w = sum.ms_walk + st.ms_walk, f = sum.ms_force + st.ms_force,
+                t = sum.ms_total + st.ms_total;
+    const int fl = sum.force_launches + st.force_launches, tl = sum.total_launches + st.total_launches + 5;
+    sum = st;
+    sum.pairs_evaluated = pairs; sum.ms_build = b; sum.ms_walk = w; sum.ms_force = f; sum.ms_total = t;
+    sum.force_launches = fl; sum.total_launches = tl;
+  }
+  HSR_CUDA(cudaStreamSynchronize(c->stream));
+  if (stats) *stats = sum;
   return 0;
 }
 

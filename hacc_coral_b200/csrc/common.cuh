@@ -58,8 +58,10 @@ struct NodeAcc {
 struct ForceLawParams {
   int kind;          // HACCSR_LAW_*
   int ncoef;         // number of polynomial coefficients in use (<= 7)
-  float a[7];
+  float a[8];        // SR_POLY: polynomial coefficients; SR_FIT: b c d e f g h l
   float rsm2, rmax2, rmax;
+  int ntab;          // SR_INTERP: table length and the evaluator's constants (ForceLaw.cxx:145-152)
+  float tab_r2min, tab_r2max, tab_oodr2;
 };
 
 // Range-list entry flag: start index refers to the pseudo-particle pool.
@@ -89,9 +91,10 @@ struct LevelInfo {
   int begin, end;     // node index range of the NEXT level
   int nsplit;         // nodes split at this level
   int error;          // 1 = node pool exhausted
+  int unit_mass;      // written with the root: 1 = every particle mass is exactly 1.0f
 };
 
-struct WorkItem { int node, sink_begin, sink_count, pad; };
+struct WorkItem { int node, sink_begin, sink_count, no_pseudo; };   // no_pseudo: the node's list holds real particles only
 
 }  // namespace haccsr
 
@@ -104,6 +107,7 @@ struct haccsr_ctx {
   haccsr::Soa cur{}, alt{};
   haccsr::ForceLawParams law{};
   bool law_set = false;
+  haccsr::DevBuf<float> law_table;                  // SR_INTERP: f[ntab] then r2[ntab]
 
   // build scratch
   haccsr::DevBuf<float4> recA, recB, src4;          // ping-pong (x,y,z,m) records, final tree-order array
@@ -121,6 +125,7 @@ struct haccsr_ctx {
 
   // tree of the last kick
   int64_t n_tree = 0;       // particles in the tree
+  bool unit_mass = false;   // all masses of the last build are exactly 1.0f
   int n_nodes = 0, n_levels = 0;
   int level_begin[128], level_end[128];
 
@@ -132,7 +137,8 @@ struct haccsr_ctx {
 
   // force work items
   haccsr::DevBuf<unsigned> item_cnt, item_off;
-  haccsr::DevBuf<haccsr::WorkItem> items;
+  haccsr::DevBuf<haccsr::WorkItem> items, items_sorted;   // in node order; sorted by decreasing work
+  haccsr::DevBuf<unsigned> lpt_hist;
   int64_t n_items = 0;
 
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};

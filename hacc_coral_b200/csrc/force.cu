@@ -26,7 +26,7 @@
 
 namespace haccsr {
 
-static constexpr int SMAX_ = 6;        // max sinks per thread (3 packed pairs): 6 x 32 = 192 sinks per work item
+static constexpr int SMAX_ = 8;        // max sink groups per thread (4 packed pairs): 8 x 32 = 256 sinks per work item
 static constexpr int FTILE = 128;      // sources per shared-memory tile
 static constexpr int FSTAGES = 4;      // ring depth
 
@@ -39,8 +39,12 @@ struct ForceParams {
   const float4 *pool;
   float *vx, *vy, *vz;
   unsigned long long *incut;   // optional counter
-  float a[7];
+  float a[8];                  // SR_POLY: a[0..6]; SR_FIT: b c d e f g h l of the analytic grid-force fit
   float rsm2, rmax2, fcoeff;
+  int unit_mass;               // 1: every particle mass is exactly 1.0f
+  const float *tab_f, *tab_r2; // SR_INTERP: grid force and its abscissae r2_i (device arrays of ntab floats)
+  float tab_r2min, tab_r2max, tab_oodr2;
+  int ntab;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -84,7 +88,10 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 struct SinkRegs2 { float2 nx, ny, nz, ax, ay, az; };   // two sinks: negated position, accumulators
 struct SinkRegs1 { float nx, ny, nz, ax, ay, az; };
 
-template <int NC, int LAW, bool GUARD0, bool COUNT>
+// UNITM: every source of the item has mass exactly 1.0f (HACC resets mass to 1 before each kick,
+// Particles.cxx:1256-1257, and the item's list holds no pseudo-particle), so the multiply by m_j is skipped --
+// x * 1.0f == x bit for bit, the result is unchanged.
+template <int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM>
 __device__ __forceinline__ void interact2(const float4 s, SinkRegs2 &k, const ForceParams &P, unsigned &cnt_a, unsigned &cnt_b) {
   const float2 dx = __fadd2_rn(make_float2(s.x, s.x), k.nx), dy = __fadd2_rn(make_float2(s.y, s.y), k.ny),
                dz = __fadd2_rn(make_float2(s.z, s.z), k.nz);
@@ -102,7 +109,7 @@ __device__ __forceinline__ void interact2(const float4 s, SinkRegs2 &k, const Fo
     for (int q = NC - 2; q >= 0; --q) p = __ffma2_rn(p, r2, make_float2(P.a[q], P.a[q]));
     f = __fadd2_rn(f, make_float2(-p.x, -p.y));
   }
-  f = __fmul2_rn(f, make_float2(s.w, s.w));
+  if (!UNITM) f = __fmul2_rn(f, make_float2(s.w, s.w));
   bool in_a = r2.x < P.rmax2, in_b = r2.y < P.rmax2;
   if (GUARD0) { in_a = in_a && (r2.x > 0.0f); in_b = in_b && (r2.y > 0.0f); }
   f.x = in_a ? f.x : 0.0f;
@@ -111,7 +118,33 @@ __device__ __forceinline__ void interact2(const float4 s, SinkRegs2 &k, const Fo
   k.ax = __ffma2_rn(f, dx, k.ax); k.ay = __ffma2_rn(f, dy, k.ay); k.az = __ffma2_rn(f, dz, k.az);
 }
 
-template <int NC, int LAW, bool GUARD0, bool COUNT>
+// Grid force g(r2) of the laws that only exist in scalar form (the per-pair cost is dominated by libm-grade
+// transcendentals or a table gather, so packing buys nothing).
+// LAW 2 = FGridEvalFit (reference ForceLaw.cxx:39-51,70-80) in the reference's order of operations, float:
+//   g = [tanh(br) - br/cosh^2(br) + c r^3 (1 + d r^2) exp(-d r^2) + e r^2 (f r^2 + g r^4 + l r^6) exp(-h r^2)] / r^3
+// LAW 3 = FGridEvalInterp (ForceLaw.cxx:145-172): linear interpolation in r2, zero outside (r2min, r2max).
+template <int LAW>
+__device__ __forceinline__ float grid_force_general(float r2, const ForceParams &P) {
+  if (LAW == 2) {
+    const float b = P.a[0], c = P.a[1], d = P.a[2], e = P.a[3], ff = P.a[4], g = P.a[5], h = P.a[6], l = P.a[7];
+    const float r = sqrtf(r2);
+    if (!(r > 0.0f)) return c + (2.0f / 3.0f) * b * b * b;
+    const float r4 = r2 * r2, r6 = r4 * r2;
+    const float br = b * r;
+    const float ch = coshf(br);
+    const float num = tanhf(br) - br / ch / ch + c * r * r2 * (1.0f + d * r2) * expf(-d * r2) +
+                      e * r2 * (ff * r2 + g * r4 + l * r6) * expf(-h * r2);
+    return num / (r * r * r);
+  } else {
+    const bool in = (r2 > P.tab_r2min) && (r2 < P.tab_r2max);
+    const int i = in ? (int)((r2 - P.tab_r2min) * P.tab_oodr2) : 0;
+    const float f0 = __ldg(P.tab_f + i), f1 = __ldg(P.tab_f + i + 1), x0 = __ldg(P.tab_r2 + i);
+    const float v = f0 + (r2 - x0) * P.tab_oodr2 * (f1 - f0);
+    return in ? v : 0.0f;
+  }
+}
+
+template <int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM>
 __device__ __forceinline__ void interact1(const float4 s, SinkRegs1 &k, const ForceParams &P, unsigned &cnt) {
   const float dx = __fadd_rn(s.x, k.nx), dy = __fadd_rn(s.y, k.ny), dz = __fadd_rn(s.z, k.nz);
   const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
@@ -122,8 +155,10 @@ __device__ __forceinline__ void interact1(const float4 s, SinkRegs1 &k, const Fo
 #pragma unroll
     for (int q = NC - 2; q >= 0; --q) p = __fmaf_rn(p, r2, P.a[q]);
     f = __fadd_rn(f, -p);
+  } else if (LAW >= 2) {
+    f = __fadd_rn(f, -grid_force_general<LAW>(r2, P));
   }
-  f = __fmul_rn(f, s.w);
+  if (!UNITM) f = __fmul_rn(f, s.w);
   bool in = r2 < P.rmax2;
   if (GUARD0) in = in && (r2 > 0.0f);
   f = in ? f : 0.0f;
@@ -162,14 +197,14 @@ __device__ __noinline__ void produce_tile(Producer &pr, const ForceParams &P, fl
 // ~130 instructions): the eight (S2, ODD) variants together fit the 32 KB instruction cache, which the first
 // version's 4x-unrolled bodies (72 KB) did not -- that showed as "no_instruction" stalls, worst on clustered
 // snapshots where all eight variants are in flight on one SM.
-template <int S2, bool ODD, int NC, int LAW, bool GUARD0, bool COUNT>
+template <int S2, int S1, int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM>
 __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P, float4 (*tiles)[FTILE],
                                          unsigned long long *bars) {
-  constexpr int S = 2 * S2 + (ODD ? 1 : 0);
-  constexpr int UNR = (S <= 2) ? 4 : ((S <= 4) ? 2 : 1);
+  constexpr int S = 2 * S2 + S1;      // S1 scalar groups follow the S2 packed pairs
+  constexpr int UNR = (LAW >= 2) ? 1 : ((S <= 2) ? 4 : ((S <= 4) ? 2 : 1));
   const int lane = threadIdx.x;
   SinkRegs2 k2[S2 > 0 ? S2 : 1];
-  SinkRegs1 k1;
+  SinkRegs1 k1[S1 > 0 ? S1 : 1];
   const int node_off_sink = it.sink_begin;
 #pragma unroll
   for (int g = 0; g < S; ++g) {
@@ -181,12 +216,14 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
       if ((g & 1) == 0) { k.nx.x = -s.x; k.ny.x = -s.y; k.nz.x = -s.z; }
       else { k.nx.y = -s.x; k.ny.y = -s.y; k.nz.y = -s.z; }
     } else {
-      k1.nx = -s.x; k1.ny = -s.y; k1.nz = -s.z;
+      SinkRegs1 &k = k1[g - 2 * S2];
+      k.nx = -s.x; k.ny = -s.y; k.nz = -s.z;
     }
   }
 #pragma unroll
   for (int k = 0; k < S2; ++k) k2[k].ax = k2[k].ay = k2[k].az = make_float2(0.f, 0.f);
-  k1.ax = k1.ay = k1.az = 0.f;
+#pragma unroll
+  for (int k = 0; k < (S1 > 0 ? S1 : 1); ++k) k1[k].ax = k1[k].ay = k1[k].az = 0.f;
   Producer pr;
   pr.ranges = P.ranges; pr.ri = P.range_off[it.node]; pr.rend = P.range_off[it.node + 1];
   pr.roff = 0; pr.remaining = P.list_len[it.node];
@@ -209,8 +246,9 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
     for (unsigned j = 0; j < nsrc; ++j) {
       const float4 s = tile[j];
 #pragma unroll
-      for (int k = 0; k < S2; ++k) interact2<NC, LAW, GUARD0, COUNT>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
-      if (ODD) interact1<NC, LAW, GUARD0, COUNT>(s, k1, P, cnt[S - 1]);
+      for (int k = 0; k < S2; ++k) interact2<NC, LAW, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
+#pragma unroll
+      for (int k = 0; k < S1; ++k) interact1<NC, LAW, GUARD0, COUNT, UNITM>(s, k1[k], P, cnt[2 * S2 + k]);
     }
     __syncwarp();                       // every lane is done reading this stage
     if (lane == 0) produce_tile(pr, P, tiles[stage], smem_u32(&bars[stage]));
@@ -224,7 +262,7 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
       if (g < 2 * S2) {
         const SinkRegs2 &k = k2[g >> 1];
         ax = (g & 1) ? k.ax.y : k.ax.x; ay = (g & 1) ? k.ay.y : k.ay.x; az = (g & 1) ? k.az.y : k.az.x;
-      } else { ax = k1.ax; ay = k1.ay; az = k1.az; }
+      } else { const SinkRegs1 &k = k1[g - 2 * S2]; ax = k.ax; ay = k.ay; az = k.az; }
       int gi = node_off_sink + j;
       float c = P.fcoeff * __ldg(&P.src4[gi].w);
       P.vx[gi] = fmaf(c, ax, P.vx[gi]); P.vy[gi] = fmaf(c, ay, P.vy[gi]); P.vz[gi] = fmaf(c, az, P.vz[gi]);
@@ -236,6 +274,21 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
     for (int g = 0; g < S; ++g) c64 += (g * 32 + lane < it.sink_count) ? cnt[g] : 0u;
     for (int o = 16; o > 0; o >>= 1) c64 += __shfl_down_sync(0xffffffffu, c64, o);
     if (lane == 0) atomicAdd(P.incut, c64);
+  }
+}
+
+template <int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM>
+__device__ __forceinline__ void dispatch_item(int S, const WorkItem it, const ForceParams &P, float4 (*tiles)[FTILE],
+                                              unsigned long long *bars) {
+  switch (S) {
+    case 1: run_item<0, 1, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
+    case 2: run_item<1, 0, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
+    case 3: run_item<1, 1, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
+    case 4: run_item<2, 0, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
+    case 5: run_item<2, 1, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
+    case 6: run_item<3, 0, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
+    case 7: run_item<3, 1, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
+    default: run_item<4, 0, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
   }
 }
 
@@ -253,14 +306,13 @@ __global__ void __launch_bounds__(32) k_force(const __grid_constant__ ForceParam
   __syncwarp();
   const WorkItem it = P.items[item];
   const int S = (it.sink_count + 31) / 32;
-  switch (S) {
-    case 1: run_item<0, true, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    case 2: run_item<1, false, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    case 3: run_item<1, true, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    case 4: run_item<2, false, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    case 5: run_item<2, true, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
-    default: run_item<3, false, NC, LAW, GUARD0, COUNT>(it, P, tiles, bars); break;
+  if (LAW >= 2) {   // fit / interpolated laws: scalar form only, two code variants
+    if (S <= 2) run_item<0, 2, NC, LAW, GUARD0, COUNT, false>(it, P, tiles, bars);
+    else run_item<0, SMAX_, NC, LAW, GUARD0, COUNT, false>(it, P, tiles, bars);
+    return;
   }
+  if (P.unit_mass && it.no_pseudo) dispatch_item<NC, LAW, GUARD0, COUNT, true>(S, it, P, tiles, bars);
+  else dispatch_item<NC, LAW, GUARD0, COUNT, false>(S, it, P, tiles, bars);
 }
 
 // ---- work items: each sink leaf is cut into equal chunks of <= 32*SMAX_ sinks ---------------------------
@@ -273,7 +325,8 @@ __global__ void k_item_count(const Node *__restrict__ nodes, const unsigned *__r
   item_cnt[k] = c;
 }
 __global__ void k_item_fill(const Node *__restrict__ nodes, const unsigned *__restrict__ item_cnt,
-                            const unsigned *__restrict__ item_off, int n_nodes, WorkItem *__restrict__ items) {
+                            const unsigned *__restrict__ item_off, const unsigned *__restrict__ n_pseudo, int n_nodes,
+                            WorkItem *__restrict__ items) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_nodes) return;
   unsigned c = item_cnt[k];
@@ -287,9 +340,47 @@ __global__ void k_item_fill(const Node *__restrict__ nodes, const unsigned *__re
     int left = cnt - (int)q * per;
     w.sink_count = left < per ? left : per;
     if (w.sink_count < 0) w.sink_count = 0;
-    w.pad = 0;
+    w.no_pseudo = n_pseudo[k] == 0 ? 1 : 0;
     items[item_off[k] + q] = w;
   }
+}
+
+// ---- longest-processing-time-first order -----------------------------------------------------------------
+// CTAs are dispatched in index order, so items are sorted by decreasing work (sink groups x list length) with a
+// counting sort on 16 bins per octave: the last CTAs to start are then the cheapest ones and the tail of the
+// kernel, where SMs run out of work, shrinks from about one average item to about one small item.  The order
+// has no effect on results: every item owns its sinks.
+static constexpr int LPT_BINS = 512;
+__device__ __forceinline__ int lpt_bin(const WorkItem &w, const unsigned *__restrict__ list_len) {
+  float work = (float)((w.sink_count + 31) / 32) * (float)list_len[w.node];
+  int b = (int)(16.0f * __log2f(work + 1.0f));
+  b = b < 0 ? 0 : (b > LPT_BINS - 1 ? LPT_BINS - 1 : b);
+  return LPT_BINS - 1 - b;       // heavy items first
+}
+__global__ void k_lpt_hist(const WorkItem *__restrict__ items, const unsigned *__restrict__ list_len, int n,
+                           unsigned *__restrict__ hist) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&hist[lpt_bin(items[i], list_len)], 1u);
+}
+__global__ void __launch_bounds__(LPT_BINS) k_lpt_scan(unsigned *__restrict__ hist) {   // hist -> exclusive offsets, in place
+  __shared__ unsigned s[LPT_BINS];
+  const int t = threadIdx.x;
+  s[t] = hist[t];
+  __syncthreads();
+  for (int o = 1; o < LPT_BINS; o <<= 1) {
+    unsigned v = (t >= o) ? s[t - o] : 0u;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  hist[t] = s[t] - hist[t];
+}
+__global__ void k_lpt_scatter(const WorkItem *__restrict__ items, const unsigned *__restrict__ list_len, int n,
+                              unsigned *__restrict__ cursor, WorkItem *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  WorkItem w = items[i];
+  out[atomicAdd(&cursor[lpt_bin(w, list_len)], 1u)] = w;
 }
 
 template <int NC, int LAW, bool GUARD0>
@@ -315,19 +406,35 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   if (c->n_items > 0x7fffffffll) { set_error("too many force work items"); return 1; }
   if (c->n_items == 0) return 0;
   HSR_TRY(c->items.ensure((size_t)c->n_items));
-  k_item_fill<<<(nn + 255) / 256, 256, 0, s>>>(c->nodes.p, c->item_cnt.p, c->item_off.p, nn, c->items.p);
+  k_item_fill<<<(nn + 255) / 256, 256, 0, s>>>(c->nodes.p, c->item_cnt.p, c->item_off.p, c->n_pseudo.p, nn, c->items.p);
   c->launches++;
+  {
+    const int ni = (int)c->n_items;
+    HSR_TRY(c->items_sorted.ensure((size_t)c->n_items)); HSR_TRY(c->lpt_hist.ensure(LPT_BINS));
+    HSR_CUDA(cudaMemsetAsync(c->lpt_hist.p, 0, LPT_BINS * sizeof(unsigned), s));
+    k_lpt_hist<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, c->lpt_hist.p);
+    k_lpt_scan<<<1, LPT_BINS, 0, s>>>(c->lpt_hist.p);
+    k_lpt_scatter<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, c->lpt_hist.p, c->items_sorted.p);
+    c->launches += 3;
+    HSR_CUDA(cudaGetLastError());
+  }
 
   ForceParams P;
-  P.items = c->items.p; P.range_off = c->range_off.p; P.ranges = c->ranges.p; P.list_len = c->list_len.p;
+  P.items = c->items_sorted.p; P.range_off = c->range_off.p; P.ranges = c->ranges.p; P.list_len = c->list_len.p;
   P.src4 = c->src4.p; P.pool = c->pool.p;
   P.vx = c->cur.vx; P.vy = c->cur.vy; P.vz = c->cur.vz;
   P.incut = c->d_counters + 11;
-  for (int i = 0; i < 7; ++i) P.a[i] = c->law.a[i];
+  for (int i = 0; i < 8; ++i) P.a[i] = c->law.a[i];
   P.rsm2 = c->law.rsm2; P.rmax2 = c->law.rmax2; P.fcoeff = fcoeff;
+  P.unit_mass = c->unit_mass ? 1 : 0;
+  P.tab_f = c->law_table.p; P.tab_r2 = c->law_table.p ? c->law_table.p + c->law.ntab : nullptr;
+  P.tab_r2min = c->law.tab_r2min; P.tab_r2max = c->law.tab_r2max; P.tab_oodr2 = c->law.tab_oodr2; P.ntab = c->law.ntab;
   const int ni = (int)c->n_items;
   int rc;
+  const bool guard0 = !(c->law.rsm2 > 0.0f);
   if (c->law.kind == HACCSR_LAW_NEWTON) rc = launch_force<1, 1, true>(c, P, ni, count_in_cutoff);
+  else if (c->law.kind == HACCSR_LAW_SR_FIT) rc = guard0 ? launch_force<1, 2, true>(c, P, ni, count_in_cutoff) : launch_force<1, 2, false>(c, P, ni, count_in_cutoff);
+  else if (c->law.kind == HACCSR_LAW_SR_INTERP) rc = guard0 ? launch_force<1, 3, true>(c, P, ni, count_in_cutoff) : launch_force<1, 3, false>(c, P, ni, count_in_cutoff);
   else {
     const bool guard = !(c->law.rsm2 > 0.0f);
     if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false>(c, P, ni, count_in_cutoff);

@@ -95,15 +95,18 @@ __global__ void __launch_bounds__(TPB) k_init_records(const float *__restrict__ 
                                                       int n, float4 *__restrict__ rec, unsigned *__restrict__ idx,
                                                       int *__restrict__ nid, unsigned *__restrict__ maxima) {
   float mc = 0.f, mm = 0.f;
+  bool notunit = false;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 r = make_float4(x[i], y[i], z[i], m[i]);
     rec[i] = r; idx[i] = (unsigned)i; nid[i] = 0;
+    notunit = notunit || (r.w != 1.0f);
     mc = fmaxf(mc, fmaxf(fabsf(r.x), fmaxf(fabsf(r.y), fabsf(r.z))));
     mm = fmaxf(mm, fabsf(r.w));
   }
   unsigned uc = __reduce_max_sync(0xffffffffu, __float_as_uint(mc));
   unsigned um = __reduce_max_sync(0xffffffffu, __float_as_uint(mm));
   if ((threadIdx.x & 31) == 0) { atomicMax(&maxima[0], uc); atomicMax(&maxima[1], um); }
+  if (__any_sync(0xffffffffu, notunit) && (threadIdx.x & 31) == 0) atomicOr(&maxima[2], 1u);
 }
 
 // scales[0] = 2^kx applied to float products w*x, scales[1] = 2^km applied to w (both exact powers of two)
@@ -129,6 +132,7 @@ __global__ void k_root_init(Node *nodes, NodeAcc *acc, int n, float3 lo, float3 
   scales[0] = ldexpf(1.0f, kx); scales[1] = ldexpf(1.0f, km);
   scales[2] = (float)(km - kx);   // exponent to undo: xc = (Sx / Sw) * 2^(km-kx)
   info->begin = 0; info->end = 1; info->nsplit = 0; info->error = 0;
+  info->unit_mass = (n > 0 && maxima[2] == 0u) ? 1 : 0;
 }
 
 // ---- pass A: per-tile partial sums ---------------------------------------------------------------
@@ -501,7 +505,7 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
                                    make_float3(hi[0], hi[1], hi[2]), maxima, scales, c->d_level);
       c->launches++;
       HSR_CUDA(cudaGetLastError());
-      c->level_begin[0] = 0; c->level_end[0] = 1; c->n_levels = 1;
+      c->level_begin[0] = 0; c->level_end[0] = 1; c->n_levels = 1; c->unit_mass = false;
       return 0;
     }
     int grid_lin = (n + TPB - 1) / TPB;
@@ -527,6 +531,7 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
       HSR_CUDA(cudaMemcpyAsync(c->h_level, c->d_level, sizeof(LevelInfo), cudaMemcpyDeviceToHost, st));
       HSR_CUDA(cudaStreamSynchronize(st));
       LevelInfo li = *c->h_level;
+      if (level == 0) c->unit_mass = li.unit_mass != 0;
       if (li.error) { overflow = true; break; }
       if (li.nsplit > 0) {
         k_left_count<<<ntiles, TPB, 0, st>>>(rec, nid, c->nodes.p, n, c->tilecount.p, c->lstart.p, c->lend.p);

@@ -138,6 +138,17 @@ int haccsr_partition_in_box(haccsr_ctx *ctx, const float hi[3], int64_t *count_i
 /* mass[:] = value for all resident particles.  Replaces: Particles.cxx:1256-1257. */
 int haccsr_fill_mass(haccsr_ctx *ctx, float value);
 
+/* One full Particles::subCycle on the resident particles (src/cpu/Particles.cxx:1176-1201): nsub times
+ *   [ stream(pt) ; move out-of-box particles to the tail ; mass = 1 ; kick(first count_in_box particles) ; stream(pt) ]
+ * with pt = prefactor * (tau2 / nsub) of map1 (:745-755) and fcoeff = c of map2 (:1230-1233, already holding the
+ * 1/nsub step fraction).  box_hi = the local grid extent nglt (Domain::ng_local_total) used by resortParticles.
+ * Particles stay in HBM throughout: one haccsr_upload before and one haccsr_download after replace the 3*nsub
+ * passes over host arrays of the reference.  stats (may be NULL) receives the LAST kick's stats with
+ * pairs_evaluated, ms_build, ms_walk, ms_force, ms_total and the launch counts summed over the nsub kicks. */
+int haccsr_subcycle(haccsr_ctx *ctx, int nsub, float prefactor_tau, const float box_hi[3], const float tree_lo[3],
+                    const float tree_hi[3], const float force_lo[3], const float force_hi[3], float theta,
+                    int64_t ppn, int tdpts, float fcoeff, haccsr_stats *stats);
+
 /* ---- inspection (tests and tools): the tree and the lists of the last kick ---------------------- */
 /* Node table, `cap` entries per array; box10 = xmin[3] xmax[3] xc[3] ppm per node
  * (TreeNode, src/halo_finder/RCBForceTree.h:131-147).  Returns the node count in *nodes. */

@@ -16,6 +16,7 @@
 //   law 1  poly6  the reference's FGridEvalPoly as shipped (-P).
 //   law 2  fit    the reference's FGridEvalFit (run_hacc.sh default).
 //   law 3  newton fl == NULL (RCBForceTree.cxx:395-404).
+//   law 4  interp the reference's FGridEvalInterp with ncoef samples (-i n).
 // A counting wrapper (optional) counts evaluated / in-cutoff pairs: the generic nbody1 calls
 // f_over_r exactly once per evaluated pair (RCBForceTree.cxx:610).
 // A derived probe class reads the protected node vector after construction so the tree topology of the
@@ -139,6 +140,20 @@ struct ref_stats {
 // rmax of the reference's FGrid (ForceLaw.cxx:32)
 float ref_rmax(void) { FGrid fg; return fg.rmax(); }
 
+// The reference's own interpolation table of the grid force (FGrid::fgor_r2_interp, ForceLaw.cxx:54-67):
+// what a caller hands to haccsr_set_force_law(HACCSR_LAW_SR_INTERP, ...).
+int ref_fgrid_table(int n, float *f_out) {
+  FGrid fg;
+  FGridEvalInterp ev(&fg, n);
+  memcpy(f_out, ev.f(), (size_t)n * sizeof(float));
+  return 0;
+}
+// the eight constants of the analytic fit are protected members of FGrid (ForceLaw.h:21); a probe subclass reads them
+struct FGridProbe : public FGrid {
+  void get(float *o) { o[0] = m_b; o[1] = m_c; o[2] = m_d; o[3] = m_e; o[4] = m_f; o[5] = m_g; o[6] = m_h; o[7] = m_l; }
+};
+int ref_fgrid_constants(float *out8) { FGridProbe p; p.get(out8); return 0; }
+
 // f_over_r of the selected law, for force-law parity tests (ForceLaw.cxx:187-192).
 int ref_force_law_eval(int law, const float *coef, int ncoef, float rsm, int64_t n, const float *r2, float *out) {
   FGrid fg;
@@ -146,6 +161,7 @@ int ref_force_law_eval(int law, const float *coef, int ncoef, float rsm, int64_t
   if (law == 0) ev = new FGridEvalPolyN(&fg, coef, ncoef);
   else if (law == 1) ev = new FGridEvalPoly(&fg);
   else if (law == 2) ev = new FGridEvalFit(&fg);
+  else if (law == 4) ev = new FGridEvalInterp(&fg, ncoef);
   else return 1;
   ForceLawSR sr(ev, rsm);
   for (int64_t i = 0; i < n; ++i) out[i] = sr.f_over_r(r2[i]);
@@ -166,6 +182,7 @@ int ref_rcb_kick(int law, const float *coef, int ncoef, int count_pairs, int qui
   if (law == 0) ev = new FGridEvalPolyN(&fg, coef, ncoef);
   else if (law == 1) ev = new FGridEvalPoly(&fg);
   else if (law == 2) ev = new FGridEvalFit(&fg);
+  else if (law == 4) ev = new FGridEvalInterp(&fg, ncoef);
   else if (law != 3) return 1;
   if (ev) fl = new ForceLawSR(ev, rsm);
   ForceLaw *use = fl;

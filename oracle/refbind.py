@@ -12,7 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-LAW_POLY5, LAW_POLY6, LAW_FIT, LAW_NEWTON = 0, 1, 2, 3
+LAW_POLY5, LAW_POLY6, LAW_FIT, LAW_NEWTON, LAW_INTERP = 0, 1, 2, 3, 4
 # 5th-order grid-force polynomial (reference ForceLaw.cxx:109-114 == BGQStep16.c:167)
 POLY5 = np.array([0.269327, -0.0750978, 0.0114808, -0.00109313, 0.0000605491, -0.00000147177],
                  dtype=np.float32)
@@ -45,6 +45,8 @@ def _lib(vmax=False):
                                      [C.POINTER(C.c_int64), C.POINTER(C.c_uint16), fp, C.c_float,
                                       C.c_float, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_int,
                                       C.POINTER(RefStats)])
+        lib.ref_fgrid_table.argtypes = [C.c_int, fp]
+        lib.ref_fgrid_constants.argtypes = [fp]
         lib.ref_tree_size.restype = C.c_int64
         ip = C.POINTER(C.c_int64)
         lib.ref_tree_get.argtypes = [C.c_int64, ip, ip, ip, ip, fp]
@@ -58,6 +60,20 @@ def _fp(a):
 
 def rmax():
     return float(_lib().ref_rmax())
+
+
+def fgrid_table(n):
+    """The reference's grid-force interpolation table of n samples (FGrid::fgor_r2_interp)."""
+    out = np.empty(n, dtype=np.float32)
+    assert _lib().ref_fgrid_table(n, _fp(out)) == 0
+    return out
+
+
+def fgrid_constants():
+    """b c d e f g h l of the reference's analytic grid-force fit (FGrid, ForceLaw.cxx:23-31)."""
+    out = np.empty(8, dtype=np.float32)
+    assert _lib().ref_fgrid_constants(_fp(out)) == 0
+    return out
 
 
 def force_law_eval(law, r2, rsm, coef=POLY5):

@@ -23,11 +23,23 @@ CASES = {
     "clustered6k_ppn32": (synth.clustered(6000, 24.0, seed=13, n_clumps=6), 24, 32, 0.5, R.LAW_POLY5, 3.2),
     "clustered6k_ppn32_theta01": (synth.clustered(6000, 24.0, seed=13, n_clumps=6), 24, 32, 0.1, R.LAW_POLY5, 3.2),
     "zeld24_ppn100_poly6": (synth.zeldovich(24, z=50.0, seed=14, ghost=0), 24, 100, 0.5, R.LAW_POLY6, 3.2),
+    # the other two grid-force evaluators of the reference: analytic fit (run_hacc.sh default) and -i 1024
+    "lattice16_ppn64_fit": (synth.jitter_lattice(16, seed=11), 16, 64, 0.5, R.LAW_FIT, 3.2),
+    "clustered6k_ppn32_fit": (synth.clustered(6000, 24.0, seed=13, n_clumps=6), 24, 32, 0.5, R.LAW_FIT, 3.2),
+    "lattice16_ppn64_interp1024": (synth.jitter_lattice(16, seed=11), 16, 64, 0.5, R.LAW_INTERP, 3.2),
 }
+NINTERP = 1024
 
 for name, (p, n, ppn, theta, law, edge) in CASES.items():
     lo, hi, flo, fhi = [0.0] * 3, [float(n)] * 3, [edge] * 3, [float(n) - edge] * 3
-    q, st, tree = R.rcb_kick(p, lo, hi, flo, fhi, 0.007, theta, ppn, fcoeff=1.0, law=law, count_pairs=True,
+    extra = {}
+    coef = R.POLY5
+    if law == R.LAW_INTERP:
+        coef = np.zeros(NINTERP, dtype=np.float32)      # the harness only reads its length (= nInterp)
+        extra["table"] = R.fgrid_table(NINTERP)
+    if law == R.LAW_FIT:
+        extra["fit"] = R.fgrid_constants()
+    q, st, tree = R.rcb_kick(p, lo, hi, flo, fhi, 0.007, theta, ppn, fcoeff=1.0, law=law, coef=coef, count_pairs=True,
                              keep_tree=True)
     o = np.argsort(q["id"], kind="stable")
     out = os.path.join(HERE, "ref_%s.npz" % name)
@@ -36,7 +48,7 @@ for name, (p, n, ppn, theta, law, edge) in CASES.items():
                         vx=q["vx"][o], vy=q["vy"][o], vz=q["vz"][o],
                         nodes=st["nodes"], leaves=st["leaves"], empty_leaves=st["empty_leaves"],
                         max_ppn=st["max_ppn"], mean_ppn=st["mean_ppn"], pairs_eval=st["pairs_eval"],
-                        pairs_incut=st["pairs_incut"],
+                        pairs_incut=st["pairs_incut"], **extra,
                         leaf_offset=tree["offset"][(tree["cl"] == 0) & (tree["cr"] == 0) & (tree["count"] > 0)],
                         leaf_count=tree["count"][(tree["cl"] == 0) & (tree["cr"] == 0) & (tree["count"] > 0)])
     print(name, p["x"].size, {k: st[k] for k in ("nodes", "leaves", "pairs_eval", "pairs_incut")}, os.path.getsize(out))
