@@ -67,6 +67,8 @@ def load_library():
     lib.haccsr_host_unregister.argtypes = [vp]
     lib.haccsr_kick.argtypes = [vp, C.c_int64, fp, fp, fp, fp, C.c_float, C.c_int64, C.c_int, C.c_float,
                                 C.POINTER(KickOpts), C.POINTER(KickStats)]
+    lib.haccsr_kick_host.argtypes = [vp, C.c_int64] + [fp] * 8 + [ip64, u16p, fp, fp, fp, fp, C.c_float, C.c_int64, C.c_int,
+                                                                  C.c_float, C.POINTER(KickOpts), C.POINTER(KickStats)]
     lib.haccsr_stream.argtypes = [vp, C.c_float]
     lib.haccsr_partition_in_box.argtypes = [vp, fp, ip64]
     lib.haccsr_fill_mass.argtypes = [vp, C.c_float]
@@ -82,7 +84,7 @@ def load_library():
 
 EXPORTS = ["haccsr_last_error", "haccsr_device_count", "haccsr_create", "haccsr_destroy", "haccsr_set_stream",
            "haccsr_set_force_law", "haccsr_upload", "haccsr_download", "haccsr_host_register",
-           "haccsr_host_unregister", "haccsr_kick", "haccsr_stream", "haccsr_partition_in_box",
+           "haccsr_host_unregister", "haccsr_kick", "haccsr_kick_host", "haccsr_stream", "haccsr_partition_in_box",
            "haccsr_fill_mass", "haccsr_subcycle", "haccsr_get_tree", "haccsr_get_lists"]
 
 _F32 = ("x", "y", "z", "vx", "vy", "vz", "mass", "phi")
@@ -161,6 +163,24 @@ class HaccSR:
         n = self.n if count is None else count
         self._check(self.lib.haccsr_kick(self._h, n, _f3(tree_lo), _f3(tree_hi), _f3(force_lo), _f3(force_hi),
                                          theta, int(ppn), tdpts, fcoeff, C.byref(opts), C.byref(st)))
+        return st.as_dict()
+
+    def kick_host(self, p, tree_lo, tree_hi, force_lo, force_hi, theta, ppn, fcoeff=1.0, count_in_cutoff=False, tdpts=1):
+        """upload + kick + download on the numpy arrays of dict `p` IN PLACE (float32 / int64 / uint16, contiguous):
+        the call a user of the reference's constructor makes."""
+        for k in _F32:
+            assert p[k].dtype == np.float32 and p[k].flags["C_CONTIGUOUS"], k
+        n = int(p["x"].size)
+        ids, mask = p.get("id"), p.get("mask")
+        st, opts = KickStats(), KickOpts()
+        opts.count_in_cutoff = int(count_in_cutoff)
+        self._check(self.lib.haccsr_kick_host(
+            self._h, n, *[_fp(p[k]) for k in _F32],
+            ids.ctypes.data_as(C.POINTER(C.c_int64)) if ids is not None else None,
+            mask.ctypes.data_as(C.POINTER(C.c_uint16)) if mask is not None else None,
+            _f3(tree_lo), _f3(tree_hi), _f3(force_lo), _f3(force_hi), theta, int(ppn), tdpts, fcoeff,
+            C.byref(opts), C.byref(st)))
+        self.n = n
         return st.as_dict()
 
     def stream(self, prefactor_tau):

@@ -134,6 +134,10 @@ int haccsr_create(haccsr_ctx **out, int device, int64_t max_particles) {
     if (cudaMallocHost((void **)&c->h_counters, 16 * sizeof(int64_t)) != cudaSuccess) { rc = 2; break; }
     if (cudaMalloc((void **)&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) { rc = 2; break; }
     for (int i = 0; i < 5; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { rc = 2; break; }
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = 2; break; }
+    if (cudaEventCreateWithFlags(&c->ev_up2, cudaEventDisableTiming) != cudaSuccess) { rc = 2; break; }
+    if (cudaEventCreateWithFlags(&c->ev_built, cudaEventDisableTiming) != cudaSuccess) { rc = 2; break; }
+    if (cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming) != cudaSuccess) { rc = 2; break; }
   } while (0);
   if (rc) {
     if (g_err[0] == 0 || rc == 2) set_error("haccsr_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -159,6 +163,10 @@ int haccsr_destroy(haccsr_ctx *c) {
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->d_counters) cudaFree(c->d_counters);
   for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->ev_up2) cudaEventDestroy(c->ev_up2);
+  if (c->ev_built) cudaEventDestroy(c->ev_built);
+  if (c->ev_main) cudaEventDestroy(c->ev_main);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return 0;
@@ -260,9 +268,11 @@ int haccsr_host_unregister(void *ptr) {
   return 0;
 }
 
-int haccsr_kick(haccsr_ctx *c, int64_t count, const float tree_lo[3], const float tree_hi[3], const float force_lo[3],
-                const float force_hi[3], float theta, int64_t ppn, int tdpts, float fcoeff,
-                const haccsr_kick_opts *opts, haccsr_stats *stats) {
+struct HostOut { float *x, *y, *z, *vx, *vy, *vz, *mass, *phi; int64_t *id; uint16_t *mask; };
+
+static int kick_impl(haccsr_ctx *c, int64_t count, const float tree_lo[3], const float tree_hi[3], const float force_lo[3],
+                     const float force_hi[3], float theta, int64_t ppn, int tdpts, float fcoeff,
+                     const haccsr_kick_opts *opts, haccsr_stats *stats, const HostOut *ho) {
   if (!c) { set_error("null context"); return 1; }
   if (!c->law_set) { set_error("haccsr_kick: force law not set"); return 1; }
   if (tdpts != 1) { set_error("haccsr_kick: only the monopole tree (TDPTS = 1, -R) is implemented; got %d", tdpts); return 1; }
@@ -281,10 +291,31 @@ int haccsr_kick(haccsr_ctx *c, int64_t count, const float tree_lo[3], const floa
   HSR_CUDA(cudaEventRecord(c->ev[0], s));
   HSR_TRY(build_tree(c, count, tree_lo, tree_hi, ppn));
   HSR_CUDA(cudaEventRecord(c->ev[1], s));
+  if (ho) {
+    // the build has permuted all ten arrays into c->cur; everything but the velocities is final now
+    cudaStream_t cs = c->copy_stream;
+    const size_t fb = (size_t)count * sizeof(float);
+    HSR_CUDA(cudaEventRecord(c->ev_built, s));
+    HSR_CUDA(cudaStreamWaitEvent(cs, c->ev_built, 0));
+    HSR_CUDA(cudaMemcpyAsync(ho->x, c->cur.x, fb, cudaMemcpyDeviceToHost, cs));
+    HSR_CUDA(cudaMemcpyAsync(ho->y, c->cur.y, fb, cudaMemcpyDeviceToHost, cs));
+    HSR_CUDA(cudaMemcpyAsync(ho->z, c->cur.z, fb, cudaMemcpyDeviceToHost, cs));
+    HSR_CUDA(cudaMemcpyAsync(ho->mass, c->cur.mass, fb, cudaMemcpyDeviceToHost, cs));
+    if (ho->phi) HSR_CUDA(cudaMemcpyAsync(ho->phi, c->cur.phi, fb, cudaMemcpyDeviceToHost, cs));
+    if (ho->id) HSR_CUDA(cudaMemcpyAsync(ho->id, c->cur.id, (size_t)count * sizeof(int64_t), cudaMemcpyDeviceToHost, cs));
+    if (ho->mask) HSR_CUDA(cudaMemcpyAsync(ho->mask, c->cur.mask, (size_t)count * sizeof(uint16_t), cudaMemcpyDeviceToHost, cs));
+  }
   HSR_TRY(build_lists(c, force_lo, force_hi, theta, st));
   HSR_CUDA(cudaEventRecord(c->ev[2], s));
   if (!skip_force) HSR_TRY(run_force(c, fcoeff, count_cut, st));
   HSR_CUDA(cudaEventRecord(c->ev[3], s));
+  if (ho) {
+    const size_t fb = (size_t)count * sizeof(float);
+    HSR_CUDA(cudaMemcpyAsync(ho->vx, c->cur.vx, fb, cudaMemcpyDeviceToHost, s));
+    HSR_CUDA(cudaMemcpyAsync(ho->vy, c->cur.vy, fb, cudaMemcpyDeviceToHost, s));
+    HSR_CUDA(cudaMemcpyAsync(ho->vz, c->cur.vz, fb, cudaMemcpyDeviceToHost, s));
+    HSR_CUDA(cudaStreamSynchronize(c->copy_stream));
+  }
   HSR_CUDA(cudaStreamSynchronize(s));
   HSR_CUDA(cudaGetLastError());
   HSR_CUDA(cudaEventElapsedTime(&st->ms_build, c->ev[0], c->ev[1]));
@@ -293,6 +324,54 @@ int haccsr_kick(haccsr_ctx *c, int64_t count, const float tree_lo[3], const floa
   HSR_CUDA(cudaEventElapsedTime(&st->ms_total, c->ev[0], c->ev[3]));
   st->force_launches = c->force_launches; st->total_launches = c->launches;
   return 0;
+}
+
+int haccsr_kick(haccsr_ctx *c, int64_t count, const float tree_lo[3], const float tree_hi[3], const float force_lo[3],
+                const float force_hi[3], float theta, int64_t ppn, int tdpts, float fcoeff,
+                const haccsr_kick_opts *opts, haccsr_stats *stats) {
+  return kick_impl(c, count, tree_lo, tree_hi, force_lo, force_hi, theta, ppn, tdpts, fcoeff, opts, stats, nullptr);
+}
+
+// upload -> kick -> download in one call, with the transfers the kernels do not depend on moved to a second
+// stream: the tree build reads only x y z mass, so vx vy vz phi id mask arrive while it runs; the force kernel
+// writes only vx vy vz, so the other seven arrays (already permuted by the build) leave while it runs.
+int haccsr_kick_host(haccsr_ctx *c, int64_t n, float *x, float *y, float *z, float *vx, float *vy, float *vz, float *mass,
+                     float *phi, int64_t *id, uint16_t *mask, const float tree_lo[3], const float tree_hi[3],
+                     const float force_lo[3], const float force_hi[3], float theta, int64_t ppn, int tdpts, float fcoeff,
+                     const haccsr_kick_opts *opts, haccsr_stats *stats) {
+  if (!c) { set_error("null context"); return 1; }
+  if (n < 0 || n > c->cap) { set_error("haccsr_kick_host: count %lld exceeds capacity %lld", (long long)n, (long long)c->cap); return 1; }
+  if (!x || !y || !z || !vx || !vy || !vz || !mass) { set_error("haccsr_kick_host: x y z vx vy vz mass are required"); return 1; }
+  if (opts && opts->skip_force) { set_error("haccsr_kick_host: skip_force is not supported here"); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream, cs = c->copy_stream;
+  const size_t fb = (size_t)n * sizeof(float);
+  // the copy stream must not run ahead of work already queued on the main stream (previous users of `cur`)
+  HSR_CUDA(cudaEventRecord(c->ev_main, s));
+  HSR_CUDA(cudaStreamWaitEvent(cs, c->ev_main, 0));
+  HSR_CUDA(cudaMemcpyAsync(c->cur.x, x, fb, cudaMemcpyHostToDevice, s));
+  HSR_CUDA(cudaMemcpyAsync(c->cur.y, y, fb, cudaMemcpyHostToDevice, s));
+  HSR_CUDA(cudaMemcpyAsync(c->cur.z, z, fb, cudaMemcpyHostToDevice, s));
+  HSR_CUDA(cudaMemcpyAsync(c->cur.mass, mass, fb, cudaMemcpyHostToDevice, s));
+  HSR_CUDA(cudaMemcpyAsync(c->cur.vx, vx, fb, cudaMemcpyHostToDevice, cs));
+  HSR_CUDA(cudaMemcpyAsync(c->cur.vy, vy, fb, cudaMemcpyHostToDevice, cs));
+  HSR_CUDA(cudaMemcpyAsync(c->cur.vz, vz, fb, cudaMemcpyHostToDevice, cs));
+  if (phi) HSR_CUDA(cudaMemcpyAsync(c->cur.phi, phi, fb, cudaMemcpyHostToDevice, cs));
+  else HSR_CUDA(cudaMemsetAsync(c->cur.phi, 0, fb, cs));
+  if (id) HSR_CUDA(cudaMemcpyAsync(c->cur.id, id, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+  else HSR_CUDA(cudaMemsetAsync(c->cur.id, 0, (size_t)n * sizeof(int64_t), cs));
+  if (mask) HSR_CUDA(cudaMemcpyAsync(c->cur.mask, mask, (size_t)n * sizeof(uint16_t), cudaMemcpyHostToDevice, cs));
+  else HSR_CUDA(cudaMemsetAsync(c->cur.mask, 0, (size_t)n * sizeof(uint16_t), cs));
+  HSR_CUDA(cudaEventRecord(c->ev_up2, cs));
+  c->wait_up2 = true;
+  c->n_resident = n;
+  // inside kick_impl the copy stream takes the seven arrays the force kernel leaves alone as soon as the build
+  // has permuted them; the velocities follow the force kernel on the main stream
+  const HostOut ho = {x, y, z, vx, vy, vz, mass, phi, id, mask};
+  int rc = kick_impl(c, n, tree_lo, tree_hi, force_lo, force_hi, theta, ppn, tdpts, fcoeff, opts, stats, &ho);
+  if (c->wait_up2) { c->wait_up2 = false; cudaStreamWaitEvent(s, c->ev_up2, 0); }   // n == 0 or an early error
+  cudaStreamSynchronize(cs);
+  return rc;
 }
 
 int haccsr_stream(haccsr_ctx *c, float pt) {

@@ -142,6 +142,11 @@ struct haccsr_ctx {
   int64_t n_items = 0;
 
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // haccsr_kick_host: second stream + events so that the copies of the arrays the tree build does not read
+  // (H2D) and of the arrays the force kernel does not write (D2H) hide behind the kernels
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_up2 = nullptr, ev_built = nullptr, ev_main = nullptr;
+  bool wait_up2 = false;    // build_tree must wait for ev_up2 before it permutes the payload arrays
   int launches = 0, force_launches = 0;
 };
 

@@ -32,7 +32,8 @@ namespace haccsr {
 
 static constexpr int TILE = 1024;      // particles per tile / thread block
 static constexpr int TPB = 256;        // threads per block in tile kernels
-static constexpr int IPT = TILE / TPB; // items per thread (striped: i = base + j*TPB + t)
+static constexpr int IPT = TILE / TPB; // items per thread (k_cm_tile: consecutive; flag/scatter passes: striped i = base + j*TPB + t)
+static_assert(IPT == 4, "k_cm_tile loads node ids as int4");
 static constexpr int SMAX = 32;        // node runs per tile accumulated in shared memory
 
 // ---- helpers ---------------------------------------------------------------------------------
@@ -176,11 +177,31 @@ __device__ __forceinline__ void flush_part(const Part &p, int nd, int n0, Slot *
   }
 }
 
+// Each thread owns IPT CONSECUTIVE particles, so a warp covers 128 consecutive particles = one or two nodes at
+// any depth; per-thread partials are combined by a segmented warp scan keyed on the node id (ids are
+// non-decreasing along the array), and only the last lane of each run touches the accumulators.  (The first
+// version striped the items over the block; at deep levels nearly every warp then straddled several nodes and
+// fell back to per-thread shared-memory atomics -- k_cm_tile was 55 % of the build, profiles/r1_launches_summary.md.)
+__device__ __forceinline__ void part_merge(Part &a, const Part &b) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { a.umin[k] = min(a.umin[k], b.umin[k]); a.umax[k] = max(a.umax[k], b.umax[k]); }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a.s[k] += b.s[k];
+}
+__device__ __forceinline__ Part part_shfl_up(const Part &p, int o) {
+  Part q;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { q.umin[k] = __shfl_up_sync(0xffffffffu, p.umin[k], o); q.umax[k] = __shfl_up_sync(0xffffffffu, p.umax[k], o); }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q.s[k] = __shfl_up_sync(0xffffffffu, p.s[k], o);
+  return q;
+}
+
 __global__ void __launch_bounds__(TPB) k_cm_tile(const float4 *__restrict__ rec, const int *__restrict__ nid, int n,
                                                  NodeAcc *__restrict__ acc, const float *__restrict__ scales) {
   __shared__ int s_n0;
   __shared__ Slot slots[SMAX];
-  const int t = threadIdx.x, base = blockIdx.x * TILE;
+  const int t = threadIdx.x, lane = t & 31, base = blockIdx.x * TILE;
   if (t == 0) s_n0 = INT_MAX;
   if (t < SMAX) {
     Slot &S = slots[t];
@@ -188,57 +209,47 @@ __global__ void __launch_bounds__(TPB) k_cm_tile(const float4 *__restrict__ rec,
     S.used = 0; S.s[0] = S.s[1] = S.s[2] = S.s[3] = 0;
   }
   __syncthreads();
-  float4 r[IPT]; int nd[IPT];
+  const int i0 = base + IPT * t;
+  int nd[IPT];
+  if (i0 + IPT <= n) {
+    const int4 v = *reinterpret_cast<const int4 *>(nid + i0);
+    nd[0] = v.x; nd[1] = v.y; nd[2] = v.z; nd[3] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) nd[j] = (i0 + j < n) ? nid[i0 + j] : -1;
+  }
   int mn = INT_MAX;
 #pragma unroll
-  for (int j = 0; j < IPT; ++j) {
-    int i = base + j * TPB + t;
-    nd[j] = (i < n) ? nid[i] : -1;
-    if (nd[j] >= 0) { r[j] = rec[i]; mn = min(mn, nd[j]); }
-  }
+  for (int j = 0; j < IPT; ++j) if (nd[j] >= 0) mn = min(mn, nd[j]);
   mn = __reduce_min_sync(0xffffffffu, mn);
-  if ((t & 31) == 0 && mn != INT_MAX) atomicMin(&s_n0, mn);
+  if (lane == 0 && mn != INT_MAX) atomicMin(&s_n0, mn);
   __syncthreads();
   const int n0 = s_n0;
   if (n0 == INT_MAX) return;   // no active particle in this tile
   const float sx = scales[0], sm = scales[1];
 
-  // fast path: the whole warp (all its items) belongs to one node -> one shuffle reduction
-  int first = nd[0];
-  bool same = true;
+  // per-thread run: the node of the thread's last active particle; particles of other nodes (a node boundary
+  // inside the thread's four) are flushed on their own
+  int key = -1;
 #pragma unroll
-  for (int j = 1; j < IPT; ++j) same = same && (nd[j] == first);
-  int f0 = __shfl_sync(0xffffffffu, first, 0);
-  bool uni = __all_sync(0xffffffffu, same && first == f0 && first >= 0);
-  if (uni) {
-    Part p; part_reset(p);
+  for (int j = 0; j < IPT; ++j) if (nd[j] >= 0) key = nd[j];
+  Part p; part_reset(p);
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) part_add(p, r[j], sx, sm);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      p.umin[k] = __reduce_min_sync(0xffffffffu, p.umin[k]);
-      p.umax[k] = __reduce_max_sync(0xffffffffu, p.umax[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) p.s[k] += __shfl_down_sync(0xffffffffu, p.s[k], o);
-    }
-    if ((t & 31) == 0) flush_part(p, f0, n0, slots, acc);
-  } else {
-    // slow path: per-thread runs (integer atomics keep the result order-independent)
-    Part p; part_reset(p);
-    int cur = -1;
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-      if (nd[j] != cur) {
-        if (cur >= 0) flush_part(p, cur, n0, slots, acc);
-        part_reset(p); cur = nd[j];
-      }
-      if (nd[j] >= 0) part_add(p, r[j], sx, sm);
-    }
-    if (cur >= 0) flush_part(p, cur, n0, slots, acc);
+  for (int j = 0; j < IPT; ++j) {
+    if (nd[j] < 0) continue;
+    const float4 r = rec[i0 + j];
+    if (nd[j] == key) part_add(p, r, sx, sm);
+    else { Part q; part_reset(q); part_add(q, r, sx, sm); flush_part(q, nd[j], n0, slots, acc); }
   }
+  // segmented inclusive scan over the warp; finished particles (key -1) form their own runs and are dropped
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const Part q = part_shfl_up(p, o);
+    const int okey = __shfl_up_sync(0xffffffffu, key, o);
+    if (lane >= o && okey == key) part_merge(p, q);
+  }
+  const int nkey = __shfl_down_sync(0xffffffffu, key, 1);
+  if (key >= 0 && (lane == 31 || nkey != key)) flush_part(p, key, n0, slots, acc);
   __syncthreads();
   if (t < SMAX && slots[t].used) {
     NodeAcc &A = acc[n0 + t];
@@ -566,6 +577,7 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
       k_moments<<<(nl + 255) / 256, 256, 0, st>>>(c->nodes.p, c->src4.p, c->level_begin[L], c->level_end[L]);
       c->launches++;
     }
+    if (c->wait_up2) { HSR_CUDA(cudaStreamWaitEvent(st, c->ev_up2, 0)); c->wait_up2 = false; }
     k_gather<<<grid_lin, 256, 0, st>>>(c->cur, c->alt, c->src4.p, c->perm.p, n);
     c->launches++;
     HSR_CUDA(cudaGetLastError());

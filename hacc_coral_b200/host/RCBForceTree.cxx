@@ -99,10 +99,10 @@ RCBForceTree<TDPTS>::RCBForceTree(POSVEL_T *minLoc, POSVEL_T *maxLoc, POSVEL_T *
   if (d.kind == HACCSR_LAW_SR_INTERP) { coef = d.table.data(); ncoef = (int)d.table.size(); }
   if (haccsr_set_force_law(ctx, d.kind, coef, ncoef, rsm, fsm) != 0) die("haccsr_set_force_law");
 
-  if (haccsr_upload(ctx, count, xLoc, yLoc, zLoc, xVel, yVel, zVel, mass, phiLoc, idLoc, maskLoc) != 0) die("haccsr_upload");
-  if (haccsr_kick(ctx, count, minLoc, maxLoc, minForceLoc, maxForceLoc, oa, nd, TDPTS, fcoeff, nullptr, &m_stats) != 0)
-    die("haccsr_kick");
-  if (haccsr_download(ctx, count, xLoc, yLoc, zLoc, xVel, yVel, zVel, mass, phiLoc, idLoc, maskLoc) != 0) die("haccsr_download");
+  // upload -> tree build, lists, force kernel, kick -> download, transfers overlapped with the kernels
+  if (haccsr_kick_host(ctx, count, xLoc, yLoc, zLoc, xVel, yVel, zVel, mass, phiLoc, idLoc, maskLoc, minLoc, maxLoc,
+                       minForceLoc, maxForceLoc, oa, nd, TDPTS, fcoeff, nullptr, &m_stats) != 0)
+    die("haccsr_kick_host");
   if (!getenv("HACCSR_QUIET")) printStats(1e-3 * m_stats.ms_build);
 }
 

@@ -126,6 +126,16 @@ int haccsr_kick(haccsr_ctx *ctx, int64_t count, const float tree_lo[3], const fl
                 const float force_lo[3], const float force_hi[3], float theta, int64_t ppn, int tdpts,
                 float fcoeff, const haccsr_kick_opts *opts, haccsr_stats *stats);
 
+/* haccsr_upload + haccsr_kick + haccsr_download in one call on caller-owned host arrays -- what the reference's
+ * constructor does to the arrays it is handed (src/cpu/Particles.cxx:1313-1338): on return all ten arrays hold the
+ * particles in tree order with vx vy vz kicked.  Transfers the kernels do not depend on run on a second stream
+ * (the build reads only x y z mass; the force kernel writes only vx vy vz), so with page-locked arrays
+ * (haccsr_host_register) most of the PCIe time hides behind the kernels.  phi, id, mask may be NULL. */
+int haccsr_kick_host(haccsr_ctx *ctx, int64_t count, float *x, float *y, float *z, float *vx, float *vy, float *vz,
+                     float *mass, float *phi, int64_t *id, uint16_t *mask, const float tree_lo[3],
+                     const float tree_hi[3], const float force_lo[3], const float force_hi[3], float theta,
+                     int64_t ppn, int tdpts, float fcoeff, const haccsr_kick_opts *opts, haccsr_stats *stats);
+
 /* x += prefactor_tau * v for all resident particles.
  * Replaces: Particles::map1 (src/cpu/Particles.cxx:732-758); prefactor_tau = prefactor * tau there. */
 int haccsr_stream(haccsr_ctx *ctx, float prefactor_tau);

@@ -313,6 +313,89 @@ def test_stream_fill_partition_helpers():
     assert np.array_equal(q["x"][:nin], out["x"][inbox])
 
 
+def test_kick_host_equals_upload_kick_download():
+    """haccsr_kick_host (transfers overlapped with the kernels on a second stream) returns bit-for-bit what the
+    three separate calls return, on pageable and on page-locked host arrays, and twice in a row."""
+    import ctypes as C
+    p = synth.clustered(30011, 24.0, seed=3)
+    rng = np.random.default_rng(1)
+    for k in ("vx", "vy", "vz", "phi"):
+        p[k] = rng.standard_normal(p["x"].size).astype(np.float32)
+    p["mask"] = (np.arange(p["x"].size) % 7).astype(np.uint16)
+    b = boxes(24)
+    ref, st, _, _ = gpu_run(p, b, 0.5, 100, fcoeff=0.25, want_tree=False, count=False)
+    g = H.HaccSR(p["x"].size)
+    g.set_force_law(H.LAW_SR_POLY, H.POLY5, RSM, H.RMAX)
+    for pinned in (False, True):
+        q = {k: np.ascontiguousarray(v).copy() for k, v in p.items()}
+        if pinned:
+            for v in q.values():
+                assert g.lib.haccsr_host_register(C.c_void_p(v.ctypes.data), v.nbytes) == 0
+        s1 = g.kick_host(q, *b, 0.5, 100, fcoeff=0.25)
+        assert s1["pairs_evaluated"] == st["pairs_evaluated"] and s1["nodes"] == st["nodes"]
+        for k in ref:
+            assert np.array_equal(q[k], ref[k]), (k, pinned)
+        s2 = g.kick_host(q, *b, 0.5, 100, fcoeff=0.25)      # second kick on the tree-ordered arrays
+        assert s2["nodes"] == st["nodes"] and np.array_equal(q["id"], ref["id"])
+        if pinned:
+            for v in q.values():
+                assert g.lib.haccsr_host_unregister(C.c_void_p(v.ctypes.data)) == 0
+    g.close()
+
+
+def test_subcycle_matches_reference_emulation(oracle):
+    """haccsr_subcycle (device-resident Particles::subCycle, reference src/cpu/Particles.cxx:1176-1201) against the
+    same loop run on the host with the oracle as the kick: nsub x [map1, out-of-box tail move, mass = 1, tree kick on
+    the in-box particles, map1].  Gate: positions after the sub-cycle within 1e-4 grid cells,
+    velocities within 1e-5 of the rms kick; the in-box count of every step must agree exactly."""
+    n, side, ppn, nsub = 24, 24, 64, 3
+    p = synth.zeldovich(n, z=50.0, seed=21, ghost=0)
+    rng = np.random.default_rng(5)
+    for k in ("vx", "vy", "vz"):
+        p[k] = (0.05 * rng.standard_normal(p["x"].size)).astype(np.float32)
+    fast = rng.choice(p["x"].size, 300, replace=False)   # these cross a face of the box during the sub-cycle
+    p["vx"][fast] = np.where(p["x"][fast] > side / 2, 4.0, -4.0).astype(np.float32)
+    p["mass"][:] = 3.0                                   # must be reset to 1 by the sub-cycle
+    pt, fcoeff = np.float32(0.4), np.float32(0.02)       # particles near the faces leave the box during the loop
+    lo, hi, flo, fhi = boxes(side)
+    g = H.HaccSR(p["x"].size)
+    g.set_force_law(H.LAW_SR_POLY, H.POLY5, RSM, H.RMAX)
+    g.upload(p)
+    st = g.subcycle(nsub, float(pt), hi, lo, hi, flo, fhi, THETA, ppn, float(fcoeff))
+    out = g.download()
+    g.close()
+    # host emulation
+    q = {k: v.copy() for k, v in p.items()}
+    pairs = 0
+    for _ in range(nsub):
+        for a, v in (("x", "vx"), ("y", "vy"), ("z", "vz")):
+            q[a] = q[a] + pt * q[v]                       # float32 multiply then add, as map1 (:753-755)
+        inbox = np.ones(q["x"].size, bool)
+        for a in ("x", "y", "z"):
+            f = np.floor(q[a])
+            inbox &= (f >= 0) & (f < side)
+        order = np.concatenate([np.nonzero(inbox)[0], np.nonzero(~inbox)[0]])
+        q = {k: v[order] for k, v in q.items()}
+        nin = int(inbox.sum())
+        q["mass"][:] = 1.0
+        head = {k: v[:nin] for k, v in q.items()}
+        o = oracle.run(head, lo, hi, flo, fhi, RSM, THETA, ppn, fcoeff=float(fcoeff))
+        pairs += o["stats"]["pairs_eval"]
+        for k in q:
+            q[k] = np.concatenate([o[k], q[k][nin:]])
+        for a, v in (("x", "vx"), ("y", "vy"), ("z", "vz")):
+            q[a] = q[a] + pt * q[v]
+    assert st["pairs_evaluated"] == pairs
+    assert int((~inbox).sum()) > 0                        # the tail move was exercised
+    a, b = by_id(out, ("x", "y", "z", "vx", "vy", "vz", "mass")), by_id(q, ("x", "y", "z", "vx", "vy", "vz", "mass"))
+    assert np.all(a["mass"] == 1.0)
+    for k in ("x", "y", "z"):
+        assert np.abs(a[k].astype(np.float64) - b[k]).max() <= 1e-4, k
+    kick = np.sqrt(sum((b[k].astype(np.float64) - by_id(p, (k,))[k]) ** 2 for k in ("vx", "vy", "vz")))
+    for k in ("vx", "vy", "vz"):
+        assert np.abs(a[k].astype(np.float64) - b[k]).max() <= 1e-5 * np.sqrt((kick ** 2).mean()) + 1e-7, k
+
+
 def test_full_size_properties():
     """BASELINE size (np = 256^3 alive + overload shell, 21.5 M particles): size-independent properties.
     (1) ids are a permutation and every array follows it; (2) no monopole is accepted at z=50 and all

@@ -93,8 +93,22 @@ __device__ __forceinline__ void pair_sink2(const float4 s, const float2 (&xi)[S2
     for (int q = 4; q >= 0; --q) p = __ffma2_rn(p, r2, make_float2(L.a[q], L.a[q]));
     // f = (f - p) * w  ->  w*f - w*p : one FMUL2 + one FFMA2 either way; keep (f - p) * w
     f = __fmul2_rn(__fadd2_rn(f, make_float2(-p.x, -p.y)), sw);
-    f.x = (r2.x < L.rmax2) ? f.x : 0.0f;
-    f.y = (r2.y < L.rmax2) ? f.y : 0.0f;
+    bool ina = r2.x < L.rmax2, inb = r2.y < L.rmax2;
+    if (EXACT == 4) {
+      // fused r2 is within 2 ulp of the unfused value: only pairs whose r2 lies within +-4 ulp of rmax2 can
+      // differ in the cutoff decision; detect them with integer compares on the float bits and redo the
+      // decision exactly (scalar mul.rn / add.rn) in a branch that is almost never taken
+      const unsigned lo = __float_as_uint(L.rmax2) - 4u;
+      bool amb = (__float_as_uint(r2.x) - lo) <= 8u;
+      amb = amb || ((__float_as_uint(r2.y) - lo) <= 8u);
+      if (__any_sync(0xffffffffu, amb)) {
+        float ea = __fadd_rn(__fadd_rn(__fmul_rn(dx.x, dx.x), __fmul_rn(dy.x, dy.x)), __fmul_rn(dz.x, dz.x));
+        float eb = __fadd_rn(__fadd_rn(__fmul_rn(dx.y, dx.y), __fmul_rn(dy.y, dy.y)), __fmul_rn(dz.y, dz.y));
+        ina = ea < L.rmax2; inb = eb < L.rmax2;
+      }
+    }
+    f.x = ina ? f.x : 0.0f;
+    f.y = inb ? f.y : 0.0f;
     ax[k] = __ffma2_rn(f, dx, ax[k]); ay[k] = __ffma2_rn(f, dy, ay[k]); az[k] = __ffma2_rn(f, dz, az[k]);
   }
 }
@@ -218,11 +232,11 @@ int main(int argc, char **argv) {
 #define RUN_SCALAR(S, E) run("scalar " #E, [&](int g, int n) { k_scalar<S, E><<<g, 32>>>(src, out, L, n); }, S, grid, nrep, peak)
 #define RUN_SINK2(S2, E, U) run("sink-packed mode" #E " unroll" #U, [&](int g, int n) { k_sink2<S2, E, U><<<g, 32>>>(src, out, L, n, zero); }, 2 * S2, grid, nrep, peak)
 #define RUN_SRC2(S, E) run("source-packed " #E, [&](int g, int n) { k_src2<S, E><<<g, 32>>>(src, out, L, n); }, S, grid, nrep, peak)
-  RUN_SCALAR(4, true); RUN_SCALAR(8, true); RUN_SCALAR(4, false); RUN_SCALAR(8, false);
+  RUN_SCALAR(8, true); RUN_SCALAR(8, false);
   const unsigned zero = (argc > 5) ? 1u : 0u;
-  RUN_SINK2(1, 2, 4); RUN_SINK2(2, 2, 4); RUN_SINK2(3, 2, 2); RUN_SINK2(4, 2, 1); RUN_SINK2(4, 2, 2); RUN_SINK2(4, 2, 4); RUN_SINK2(6, 2, 1);
+  RUN_SINK2(1, 4, 4); RUN_SINK2(2, 4, 4); RUN_SINK2(3, 4, 2); RUN_SINK2(3, 4, 1); RUN_SINK2(4, 4, 1); RUN_SINK2(4, 4, 2);
   RUN_SINK2(1, 3, 4); RUN_SINK2(2, 3, 4); RUN_SINK2(3, 3, 2); RUN_SINK2(4, 3, 1); RUN_SINK2(4, 3, 2); RUN_SINK2(4, 3, 4); RUN_SINK2(6, 3, 1);
   RUN_SINK2(1, 0, 4); RUN_SINK2(2, 0, 4); RUN_SINK2(3, 0, 2); RUN_SINK2(4, 0, 1); RUN_SINK2(4, 0, 2); RUN_SINK2(4, 0, 4); RUN_SINK2(6, 0, 1);
-  RUN_SRC2(2, true); RUN_SRC2(4, true); RUN_SRC2(6, true); RUN_SRC2(8, true); RUN_SRC2(4, false); RUN_SRC2(8, false);
+  RUN_SRC2(4, true);
   return 0;
 }

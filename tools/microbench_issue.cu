@@ -62,13 +62,15 @@ static void run(const char *name, int nsm, float *out, long long *d_cyc) {
   CK(cudaEventSynchronize(e1));
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
   long long cyc; CK(cudaMemcpy(&cyc, d_cyc, sizeof(cyc), cudaMemcpyDeviceToHost));
-  // per scheduler: 8 warps, each runs `iters` iterations
-  double cyc_per_iter_sched = (double)cyc / iters / 1.0;           // cycles for one warp-iteration turn of all 8 warps
-  double per_warp_iter = cyc_per_iter_sched / 8.0;                 // scheduler cycles per warp-iteration
-  int lane_fma = PACKED ? 2 * NF : 2 * NF;                         // FMA-pipe lane-cycles per warp-iteration
+  // whole-kernel view: every scheduler (4 per SM) serves grid*8/(4*nsm) warps, each running `iters` iterations
+  const double warps_per_sched = (double)grid * 8.0 / (4.0 * nsm);
+  const double sched_cycles = ms * 1e-3 * 1965e6;                  // at the 1965 MHz the sampler reports under load
+  const double per_warp_iter = sched_cycles / (iters * warps_per_sched);
+  int lane_fma = 2 * NF;                                           // FMA-pipe lane-cycles per warp-iteration
   int instr = (PACKED ? NF : 2 * NF) + 2 * NA + NM;
-  printf("%-34s FMAlane=%2d instr=%2d : %.2f cycles/warp-iter (%.2f per lane-FMA-cycle) eff clock %.0f MHz\n", name, lane_fma, instr,
-         per_warp_iter, per_warp_iter / lane_fma, (double)cyc / (ms * 1e3));
+  int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mix<PACKED, NF, NA, NM>, 256, 0));
+  printf("%-34s FMAlane=%2d instr=%2d : %.2f cycles/warp-iter (%.2f per lane-FMA-cycle, %.2f per instr) block0 clock %.0f MHz occ %d\n", name, lane_fma, instr,
+         per_warp_iter, per_warp_iter / lane_fma, per_warp_iter / instr, (double)cyc / (ms * 1e3), occ);
 }
 
 int main() {
@@ -79,6 +81,7 @@ int main() {
   CK(cudaMalloc(&d_cyc, sizeof(long long)));
   const int n = prop.multiProcessorCount;
 #define R(P, NF, NA, NM) run<P, NF, NA, NM>(#P " NF=" #NF " NA=" #NA " NM=" #NM, n, out, d_cyc)
+  R(false, 16, 0, 0); R(true, 16, 0, 0);
   R(false, 8, 0, 0); R(true, 8, 0, 0);
   R(false, 8, 1, 0); R(true, 8, 1, 0);
   R(false, 8, 2, 0); R(true, 8, 2, 0);
