@@ -75,6 +75,13 @@ def load_library():
     lib.haccsr_subcycle.argtypes = [vp, C.c_int, C.c_float, fp, fp, fp, fp, fp, C.c_float, C.c_int64, C.c_int, C.c_float,
                                     C.POINTER(KickStats)]
     i32p = C.POINTER(C.c_int32)
+    lib.haccsr_refresh_message_bytes.restype = C.c_int64
+    lib.haccsr_refresh_message_bytes.argtypes = [C.c_int64]
+    lib.haccsr_refresh_begin.argtypes = [vp, fp, fp, C.c_float, i32p, ip64, ip64]
+    lib.haccsr_refresh_pack.argtypes = [vp, ip64, vp]
+    lib.haccsr_refresh_append.argtypes = [vp, vp, C.c_int64]
+    lib.haccsr_resident.restype = C.c_int64
+    lib.haccsr_resident.argtypes = [vp]
     lib.haccsr_get_tree.argtypes = [vp, C.c_int64, ip64, i32p, i32p, i32p, i32p, fp]
     u32p = C.POINTER(C.c_uint32)
     lib.haccsr_get_lists.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, ip64, ip64, ip64, u32p, u32p, fp]
@@ -85,7 +92,8 @@ def load_library():
 EXPORTS = ["haccsr_last_error", "haccsr_device_count", "haccsr_create", "haccsr_destroy", "haccsr_set_stream",
            "haccsr_set_force_law", "haccsr_upload", "haccsr_download", "haccsr_host_register",
            "haccsr_host_unregister", "haccsr_kick", "haccsr_kick_host", "haccsr_stream", "haccsr_partition_in_box",
-           "haccsr_fill_mass", "haccsr_subcycle", "haccsr_get_tree", "haccsr_get_lists"]
+           "haccsr_fill_mass", "haccsr_subcycle", "haccsr_refresh_message_bytes", "haccsr_refresh_begin",
+           "haccsr_refresh_pack", "haccsr_refresh_append", "haccsr_resident", "haccsr_get_tree", "haccsr_get_lists"]
 
 _F32 = ("x", "y", "z", "vx", "vy", "vz", "mass", "phi")
 
@@ -108,6 +116,8 @@ class HaccSR:
         self._check(self.lib.haccsr_create(C.byref(h), device, int(max_particles)))
         self._h = h
         self.n = 0
+        self.device = device
+        self.torch_device = "cuda:%d" % device
 
     def _check(self, rc):
         if rc != 0:
@@ -200,6 +210,31 @@ class HaccSR:
         self._check(self.lib.haccsr_subcycle(self._h, int(nsub), prefactor_tau, _f3(box_hi), _f3(tree_lo), _f3(tree_hi),
                                              _f3(force_lo), _f3(force_hi), theta, int(ppn), tdpts, fcoeff, C.byref(st)))
         return st.as_dict()
+
+    # ---- overload refresh (device part; hacc_coral_b200/refresh.py drives it) ----
+    def refresh_message_bytes(self, n):
+        return int(self.lib.haccsr_refresh_message_bytes(int(n)))
+
+    def refresh_begin(self, alive_lo, alive_hi, ol, slot_of_dir):
+        sod = np.ascontiguousarray(slot_of_dir, dtype=np.int32)
+        counts = np.zeros(27, dtype=np.int64)
+        nal = C.c_int64()
+        self._check(self.lib.haccsr_refresh_begin(self._h, _f3(alive_lo), _f3(alive_hi), ol,
+                                                  sod.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                  counts.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nal)))
+        self.n = nal.value
+        return counts, nal.value
+
+    def refresh_pack(self, byte_off_by_slot, sendbuf_ptr):
+        off = np.ascontiguousarray(byte_off_by_slot, dtype=np.int64)
+        self._check(self.lib.haccsr_refresh_pack(self._h, off.ctypes.data_as(C.POINTER(C.c_int64)), C.c_void_p(sendbuf_ptr)))
+
+    def refresh_append(self, message_ptr, n):
+        self._check(self.lib.haccsr_refresh_append(self._h, C.c_void_p(message_ptr), int(n)))
+        self.n = self.resident()
+
+    def resident(self):
+        return int(self.lib.haccsr_resident(self._h))
 
     def tree(self):
         nn = C.c_int64()

@@ -82,6 +82,19 @@ static int lin_grid(const haccsr_ctx *c, int64_t n) {
   return (int)g;
 }
 
+// stable two-way partition of all ten arrays: flagged particles first (in order), the rest behind them (in order)
+int compact_by_flags(haccsr_ctx *c, const unsigned *flag, unsigned *pref, int64_t n, int64_t *n_kept) {
+  HSR_TRY(scan_exclusive(c, flag, pref, n, c->d_counters + 12));
+  HSR_CUDA(cudaMemcpyAsync(c->h_counters + 12, c->d_counters + 12, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  HSR_CUDA(cudaStreamSynchronize(c->stream));
+  const int64_t nin = c->h_counters[12];
+  k_compact<<<lin_grid(c, n), 256, 0, c->stream>>>(c->cur, c->alt, flag, pref, (unsigned)nin, (long long)n);
+  HSR_CUDA(cudaGetLastError());
+  Soa t = c->cur; c->cur = c->alt; c->alt = t;
+  if (n_kept) *n_kept = nin;
+  return 0;
+}
+
 }  // namespace haccsr
 
 using namespace haccsr;
@@ -157,7 +170,7 @@ int haccsr_destroy(haccsr_ctx *c) {
   c->nidA.release(); c->nidB.release(); c->nodes.release(); c->acc.release(); c->lstart.release(); c->lend.release();
   c->lbase.release(); c->nleft.release(); c->tilecount.release(); c->tilebase.release(); c->scratch_u32.release();
   c->n_ranges.release(); c->n_pseudo.release(); c->range_off.release(); c->pseudo_off.release(); c->list_len.release();
-  c->ranges.release(); c->pool.release(); c->law_table.release(); c->item_cnt.release(); c->item_off.release(); c->items.release(); c->items_sorted.release(); c->lpt_hist.release();
+  c->ranges.release(); c->pool.release(); c->law_table.release(); c->item_cnt.release(); c->item_off.release(); c->items.release(); c->items_sorted.release(); c->lpt_hist.release(); c->refresh_slots.release();
   if (c->h_level) cudaFreeHost(c->h_level);
   if (c->d_level) cudaFree(c->d_level);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -400,15 +413,9 @@ int haccsr_partition_in_box(haccsr_ctx *c, const float hi[3], int64_t *count_in_
   if (n == 0) { if (count_in_box) *count_in_box = 0; return 0; }
   // flags / prefixes borrow the build's index buffers (they are rebuilt by every kick)
   HSR_TRY(c->idxA.ensure((size_t)n + 1)); HSR_TRY(c->idxB.ensure((size_t)n + 1));
-  const int g = lin_grid(c, n);
-  k_inbox_flags<<<g, 256, 0, c->stream>>>(c->cur.x, c->cur.y, c->cur.z, make_float3(hi[0], hi[1], hi[2]), (long long)n, c->idxA.p);
-  HSR_TRY(scan_exclusive(c, c->idxA.p, c->idxB.p, n, c->d_counters + 12));
-  HSR_CUDA(cudaMemcpyAsync(c->h_counters + 12, c->d_counters + 12, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-  HSR_CUDA(cudaStreamSynchronize(c->stream));
-  const int64_t nin = c->h_counters[12];
-  k_compact<<<g, 256, 0, c->stream>>>(c->cur, c->alt, c->idxA.p, c->idxB.p, (unsigned)nin, (long long)n);
-  HSR_CUDA(cudaGetLastError());
-  Soa t = c->cur; c->cur = c->alt; c->alt = t;
+  k_inbox_flags<<<lin_grid(c, n), 256, 0, c->stream>>>(c->cur.x, c->cur.y, c->cur.z, make_float3(hi[0], hi[1], hi[2]), (long long)n, c->idxA.p);
+  int64_t nin = 0;
+  HSR_TRY(compact_by_flags(c, c->idxA.p, c->idxB.p, n, &nin));
   if (count_in_box) *count_in_box = nin;
   return 0;
 }

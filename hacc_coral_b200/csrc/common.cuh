@@ -144,6 +144,13 @@ struct haccsr_ctx {
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // haccsr_kick_host: second stream + events so that the copies of the arrays the tree build does not read
   // (H2D) and of the arrays the force kernel does not write (D2H) hide behind the kernels
+  // overload refresh (refresh.cu): state kept between haccsr_refresh_begin and haccsr_refresh_pack
+  int64_t refresh_m = 0;                     // candidates (alive particles within the overload width of a face)
+  int refresh_ntiles = 0;
+  float refresh_alo[3] = {0, 0, 0}, refresh_ahi[3] = {0, 0, 0}, refresh_ol = 0.f;
+  int refresh_slot_of_dir[27] = {0};
+  int64_t refresh_count[27] = {0};
+  haccsr::DevBuf<int> refresh_slots;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_up2 = nullptr, ev_built = nullptr, ev_main = nullptr;
   bool wait_up2 = false;    // build_tree must wait for ev_up2 before it permutes the payload arrays
@@ -157,6 +164,8 @@ int build_tree(haccsr_ctx *c, int64_t n, const float lo[3], const float hi[3], i
 int build_lists(haccsr_ctx *c, const float flo[3], const float fhi[3], float theta, haccsr_stats *st);
 // force.cu
 int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *st);
+// api.cu: stable two-way partition of the ten arrays by a 0/1 flag
+int compact_by_flags(haccsr_ctx *c, const unsigned *flag, unsigned *pref, int64_t n, int64_t *n_kept);
 // scan utility (tree_build.cu): exclusive scan of n unsigned values; total written to *d_total (device).
 int scan_exclusive(haccsr_ctx *c, const unsigned *in, unsigned *out, int64_t n, unsigned long long *d_total);
 }  // namespace haccsr

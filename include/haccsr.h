@@ -159,6 +159,30 @@ int haccsr_subcycle(haccsr_ctx *ctx, int nsub, float prefactor_tau, const float 
                     const float tree_hi[3], const float force_lo[3], const float force_hi[3], float theta,
                     int64_t ppn, int tdpts, float fcoeff, haccsr_stats *stats);
 
+/* ---- overload (ghost-zone) refresh: the per-rank, on-device part ---------------------------------------------------
+ * Replaces ParticleExchange::exchangeParticles as driven by MC3Extras::refreshParticles at refresh steps
+ * (src/simulation/MC3Extras.cxx:660-706; src/halo_finder/ParticleExchange.cxx:488-762), in the local grid units
+ * of the tree.  Directions are numbered d = (sx+1)*9 + (sy+1)*3 + (sz+1), s in {-1,0,1}^3, d != 13; the caller
+ * maps each direction to a message SLOT (0..25) so that the send buffer is ordered by destination rank.
+ *
+ *   haccsr_refresh_begin   drops the ghosts (keeps x in [alive_lo, alive_hi), Particles.cxx:975), finds the alive
+ *                          particles that are ghosts of each neighbour (inclusive slabs of width ol,
+ *                          ParticleExchange.cxx:280-450,549-565) and returns the particle count of every message;
+ *   haccsr_refresh_pack    writes the 26 messages into a device buffer at the byte offsets the caller chose, each
+ *                          haccsr_refresh_message_bytes(n) long: id[n] | x y z vx vy vz mass phi [n] | mask[n];
+ *                          positions are already in the receiver's frame (x - s * (alive_hi - alive_lo), the
+ *                          reference's +-boxSize wrap of :672-673 included);
+ *   (transport between ranks: one all-to-all-v of the buffer over NCCL -- hacc_coral_b200/refresh.py -- or MPI)
+ *   haccsr_refresh_append  appends one received message (device pointer) behind the resident particles.
+ * Messages keep the sender's particle order, so the result is deterministic. */
+int64_t haccsr_refresh_message_bytes(int64_t n);
+int haccsr_refresh_begin(haccsr_ctx *ctx, const float alive_lo[3], const float alive_hi[3], float ol,
+                         const int32_t slot_of_dir[27], int64_t counts_by_slot[27], int64_t *n_alive);
+int haccsr_refresh_pack(haccsr_ctx *ctx, const int64_t byte_off_by_slot[27], void *sendbuf_device);
+int haccsr_refresh_append(haccsr_ctx *ctx, const void *message_device, int64_t n);
+/* Number of particles currently resident in the context. */
+int64_t haccsr_resident(haccsr_ctx *ctx);
+
 /* ---- inspection (tests and tools): the tree and the lists of the last kick ---------------------- */
 /* Node table, `cap` entries per array; box10 = xmin[3] xmax[3] xc[3] ppm per node
  * (TreeNode, src/halo_finder/RCBForceTree.h:131-147).  Returns the node count in *nodes. */
