@@ -8,6 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 LAW_SR_POLY, LAW_SR_FIT, LAW_SR_INTERP, LAW_NEWTON = 0, 1, 2, 3
+ARITH_FUSED, ARITH_X86 = 0, 1       # include/haccsr.h HACCSR_ARITH_*
 # reference src/halo_finder/ForceLaw.cxx:109-114 (== BGQStep16.c:167) and :98-104
 POLY5 = np.array([0.269327, -0.0750978, 0.0114808, -0.00109313, 0.0000605491, -0.00000147177], dtype=np.float32)
 POLY6 = np.array([0.271431, -0.0783394, 0.0133122, -0.00159485, 0.000132336, -0.00000663394, 0.000000147305],
@@ -61,6 +62,7 @@ def load_library():
     lib.haccsr_destroy.argtypes = [vp]
     lib.haccsr_set_stream.argtypes = [vp, vp]
     lib.haccsr_set_force_law.argtypes = [vp, C.c_int, fp, C.c_int, C.c_float, C.c_float]
+    lib.haccsr_set_arithmetic.argtypes = [vp, C.c_int]
     lib.haccsr_upload.argtypes = [vp, C.c_int64] + [fp] * 8 + [ip64, u16p]
     lib.haccsr_download.argtypes = [vp, C.c_int64] + [fp] * 8 + [ip64, u16p]
     lib.haccsr_host_register.argtypes = [vp, C.c_size_t]
@@ -90,7 +92,7 @@ def load_library():
 
 
 EXPORTS = ["haccsr_last_error", "haccsr_device_count", "haccsr_create", "haccsr_destroy", "haccsr_set_stream",
-           "haccsr_set_force_law", "haccsr_upload", "haccsr_download", "haccsr_host_register",
+           "haccsr_set_force_law", "haccsr_set_arithmetic", "haccsr_upload", "haccsr_download", "haccsr_host_register",
            "haccsr_host_unregister", "haccsr_kick", "haccsr_kick_host", "haccsr_stream", "haccsr_partition_in_box",
            "haccsr_fill_mass", "haccsr_subcycle", "haccsr_refresh_message_bytes", "haccsr_refresh_begin",
            "haccsr_refresh_pack", "haccsr_refresh_append", "haccsr_resident", "haccsr_get_tree", "haccsr_get_lists"]
@@ -109,12 +111,14 @@ def _f3(v):
 class HaccSR:
     """One context on one GPU: upload -> [stream, kick, stream]* -> download."""
 
-    def __init__(self, max_particles, device=0):
+    def __init__(self, max_particles, device=0, arith=None):
         self.lib = load_library()
         h = C.c_void_p()
         self._h = None
         self._check(self.lib.haccsr_create(C.byref(h), device, int(max_particles)))
         self._h = h
+        if arith is not None:
+            self.set_arithmetic(arith)
         self.n = 0
         self.device = device
         self.torch_device = "cuda:%d" % device
@@ -136,6 +140,9 @@ class HaccSR:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.haccsr_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_arithmetic(self, mode):
+        self._check(self.lib.haccsr_set_arithmetic(self._h, int(mode)))
 
     def set_force_law(self, kind=LAW_SR_POLY, coeffs=POLY5, rsm=0.007, rmax=RMAX):
         coeffs = np.ascontiguousarray(coeffs if coeffs is not None else [], dtype=np.float32)

@@ -230,7 +230,29 @@ int haccsr_set_force_law(haccsr_ctx *c, int kind, const float *coeffs, int ncoef
   c->law.rsm2 = (kind == HACCSR_LAW_NEWTON) ? 0.0f : rsm * rsm;   // ForceLaw.cxx:177 (m_rsm2 = rsm*rsm, float)
   c->law.rmax = rmax;
   c->law.rmax2 = rmax * rmax;                                     // RCBForceTree.cxx:582 (float product)
+  c->law.smax = c->law.rmax2 + c->law.rsm2;
+  if (kind == HACCSR_LAW_SR_POLY) {
+    // HACCSR_ARITH_FUSED evaluates the polynomial in s = r2 + eps, eps = rsm2:  sum_j a_j (s - eps)^j = sum_k b_k s^k,
+    // b_k = sum_{j>=k} a_j C(j,k) (-eps)^(j-k), accumulated in double from j = k upwards, rounded once to float.
+    const double eps = (double)c->law.rsm2;
+    for (int k = 0; k < ncoef; ++k) {
+      double acc = 0.0, binom = 1.0, pw = 1.0;        // C(j,k), (-eps)^(j-k)
+      for (int j = k; j < ncoef; ++j) {
+        acc += (double)coeffs[j] * binom * pw;
+        binom = binom * (double)(j + 1) / (double)(j + 1 - k);
+        pw *= -eps;
+      }
+      c->law.b[k] = (float)acc;
+    }
+  }
   c->law_set = true;
+  return 0;
+}
+
+int haccsr_set_arithmetic(haccsr_ctx *c, int mode) {
+  if (!c) { set_error("null context"); return 1; }
+  if (mode != HACCSR_ARITH_FUSED && mode != HACCSR_ARITH_X86) { set_error("unknown arithmetic mode %d", mode); return 1; }
+  c->arith = mode;
   return 0;
 }
 

@@ -59,7 +59,8 @@ struct ForceLawParams {
   int kind;          // HACCSR_LAW_*
   int ncoef;         // number of polynomial coefficients in use (<= 7)
   float a[8];        // SR_POLY: polynomial coefficients; SR_FIT: b c d e f g h l
-  float rsm2, rmax2, rmax;
+  float b[8];        // SR_POLY: the polynomial re-expanded in s = r2 + rsm2 (HACCSR_ARITH_FUSED)
+  float rsm2, rmax2, rmax, smax;   // smax = rmax2 + rsm2
   int ntab;          // SR_INTERP: table length and the evaluator's constants (ForceLaw.cxx:145-152)
   float tab_r2min, tab_r2max, tab_oodr2;
 };
@@ -107,6 +108,7 @@ struct haccsr_ctx {
   haccsr::Soa cur{}, alt{};
   haccsr::ForceLawParams law{};
   bool law_set = false;
+  int arith = HACCSR_ARITH_FUSED;
   haccsr::DevBuf<float> law_table;                  // SR_INTERP: f[ntab] then r2[ntab]
 
   // build scratch

@@ -40,7 +40,8 @@ struct ForceParams {
   float *vx, *vy, *vz;
   unsigned long long *incut;   // optional counter
   float a[8];                  // SR_POLY: a[0..6]; SR_FIT: b c d e f g h l of the analytic grid-force fit
-  float rsm2, rmax2, fcoeff;
+  float b[8];                  // SR_POLY, fused arithmetic: MINUS the polynomial re-expanded in s = r2 + rsm^2
+  float rsm2, rmax2, smax, fcoeff;   // smax = rmax2 + rsm2: the cutoff on s
   int unit_mass;               // 1: every particle mass is exactly 1.0f
   const float *tab_f, *tab_r2; // SR_INTERP: grid force and its abscissae r2_i (device arrays of ntab floats)
   float tab_r2min, tab_r2max, tab_oodr2;
@@ -91,6 +92,50 @@ struct SinkRegs1 { float nx, ny, nz, ax, ay, az; };
 // UNITM: every source of the item has mass exactly 1.0f (HACC resets mass to 1 before each kick,
 // Particles.cxx:1256-1257, and the item's list holds no pseudo-particle), so the multiply by m_j is skipped --
 // x * 1.0f == x bit for bit, the result is unchanged.
+// FUSED (HACCSR_ARITH_FUSED, SR_POLY only): the contracted arithmetic of the reference's production kernel --
+// the QPX loop forms r2 with three multiply-adds (BGQStep16.c:76-86) -- taken one step further:
+//   s  = fma(dz,dz, fma(dy,dy, fma(dx,dx, rsm^2)))        the chain is seeded with rsm^2, so it yields r2 + rsm^2;
+//   -g = Horner in s with P.b = MINUS the law's polynomial re-expanded about -rsm^2 (in double, on the host);
+//   f  = fma(rs*rs, rs, -g), rs = rsqrt(s)                 s^-3/2 and the subtraction in one multiply and one FMA;
+//   cutoff s < P.smax (= rmax^2 + rsm^2) as the predicate of three scalar FFMAs per sink -- no select.
+// 16 FMA-pipe operations and 2 other instructions (MUFU, FSETP) per pair instead of 20 + 3.  On sm_100 an FFMA2
+// occupies the issue port for two cycles, so every instruction saved shows (tools/microbench_force.cu, modes 3/5/6/7:
+// 58.7 / 70.5 / 72.7 / 75.4 % of the FP32 peak).  Oracle form FORM_FUSED restates exactly this sequence.
+template <int NC, bool GUARD0, bool COUNT, bool UNITM>
+__device__ __forceinline__ void interact2_fused(const float4 s, SinkRegs2 &k, const ForceParams &P, unsigned &cnt_a, unsigned &cnt_b) {
+  const float2 dx = __fadd2_rn(make_float2(s.x, s.x), k.nx), dy = __fadd2_rn(make_float2(s.y, s.y), k.ny),
+               dz = __fadd2_rn(make_float2(s.z, s.z), k.nz);
+  float2 t = __ffma2_rn(dx, dx, make_float2(P.rsm2, P.rsm2));
+  t = __ffma2_rn(dy, dy, t);
+  t = __ffma2_rn(dz, dz, t);
+  float2 p = make_float2(P.b[NC - 1], P.b[NC - 1]);
+#pragma unroll
+  for (int q = NC - 2; q >= 0; --q) p = __ffma2_rn(p, t, make_float2(P.b[q], P.b[q]));
+  const float2 rs = make_float2(rsqrt_ftz(t.x), rsqrt_ftz(t.y));
+  float2 f = __ffma2_rn(__fmul2_rn(rs, rs), rs, p);
+  if (!UNITM) f = __fmul2_rn(f, make_float2(s.w, s.w));
+  bool in_a = t.x < P.smax, in_b = t.y < P.smax;
+  if (GUARD0) { in_a = in_a && (t.x > P.rsm2); in_b = in_b && (t.y > P.rsm2); }
+  if (in_a) { k.ax.x = __fmaf_rn(f.x, dx.x, k.ax.x); k.ay.x = __fmaf_rn(f.x, dy.x, k.ay.x); k.az.x = __fmaf_rn(f.x, dz.x, k.az.x); }
+  if (in_b) { k.ax.y = __fmaf_rn(f.y, dx.y, k.ax.y); k.ay.y = __fmaf_rn(f.y, dy.y, k.ay.y); k.az.y = __fmaf_rn(f.y, dz.y, k.az.y); }
+  if (COUNT) { cnt_a += (in_a && t.x > P.rsm2) ? 1u : 0u; cnt_b += (in_b && t.y > P.rsm2) ? 1u : 0u; }
+}
+template <int NC, bool GUARD0, bool COUNT, bool UNITM>
+__device__ __forceinline__ void interact1_fused(const float4 s, SinkRegs1 &k, const ForceParams &P, unsigned &cnt) {
+  const float dx = __fadd_rn(s.x, k.nx), dy = __fadd_rn(s.y, k.ny), dz = __fadd_rn(s.z, k.nz);
+  const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, P.rsm2)));
+  float p = P.b[NC - 1];
+#pragma unroll
+  for (int q = NC - 2; q >= 0; --q) p = __fmaf_rn(p, t, P.b[q]);
+  const float rs = rsqrt_ftz(t);
+  float f = __fmaf_rn(__fmul_rn(rs, rs), rs, p);
+  if (!UNITM) f = __fmul_rn(f, s.w);
+  bool in = t < P.smax;
+  if (GUARD0) in = in && (t > P.rsm2);
+  if (in) { k.ax = __fmaf_rn(f, dx, k.ax); k.ay = __fmaf_rn(f, dy, k.ay); k.az = __fmaf_rn(f, dz, k.az); }
+  if (COUNT) cnt += (in && t > P.rsm2) ? 1u : 0u;
+}
+
 template <int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM>
 __device__ __forceinline__ void interact2(const float4 s, SinkRegs2 &k, const ForceParams &P, unsigned &cnt_a, unsigned &cnt_b) {
   const float2 dx = __fadd2_rn(make_float2(s.x, s.x), k.nx), dy = __fadd2_rn(make_float2(s.y, s.y), k.ny),
@@ -197,7 +242,7 @@ __device__ __noinline__ void produce_tile(Producer &pr, const ForceParams &P, fl
 // ~130 instructions): the eight (S2, ODD) variants together fit the 32 KB instruction cache, which the first
 // version's 4x-unrolled bodies (72 KB) did not -- that showed as "no_instruction" stalls, worst on clustered
 // snapshots where all eight variants are in flight on one SM.
-template <int S2, int S1, int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM>
+template <int S2, int S1, int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM, bool FUSED>
 __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P, float4 (*tiles)[FTILE],
                                          unsigned long long *bars) {
   constexpr int S = 2 * S2 + S1;      // S1 scalar groups follow the S2 packed pairs
@@ -246,9 +291,15 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
     for (unsigned j = 0; j < nsrc; ++j) {
       const float4 s = tile[j];
 #pragma unroll
-      for (int k = 0; k < S2; ++k) interact2<NC, LAW, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
+      for (int k = 0; k < S2; ++k) {
+        if (FUSED) interact2_fused<NC, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
+        else interact2<NC, LAW, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
+      }
 #pragma unroll
-      for (int k = 0; k < S1; ++k) interact1<NC, LAW, GUARD0, COUNT, UNITM>(s, k1[k], P, cnt[2 * S2 + k]);
+      for (int k = 0; k < S1; ++k) {
+        if (FUSED) interact1_fused<NC, GUARD0, COUNT, UNITM>(s, k1[k], P, cnt[2 * S2 + k]);
+        else interact1<NC, LAW, GUARD0, COUNT, UNITM>(s, k1[k], P, cnt[2 * S2 + k]);
+      }
     }
     __syncwarp();                       // every lane is done reading this stage
     if (lane == 0) produce_tile(pr, P, tiles[stage], smem_u32(&bars[stage]));
@@ -277,22 +328,22 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
   }
 }
 
-template <int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM>
+template <int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM, bool FUSED>
 __device__ __forceinline__ void dispatch_item(int S, const WorkItem it, const ForceParams &P, float4 (*tiles)[FTILE],
                                               unsigned long long *bars) {
   switch (S) {
-    case 1: run_item<0, 1, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
-    case 2: run_item<1, 0, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
-    case 3: run_item<1, 1, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
-    case 4: run_item<2, 0, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
-    case 5: run_item<2, 1, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
-    case 6: run_item<3, 0, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
-    case 7: run_item<3, 1, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
-    default: run_item<4, 0, NC, LAW, GUARD0, COUNT, UNITM>(it, P, tiles, bars); break;
+    case 1: run_item<0, 1, NC, LAW, GUARD0, COUNT, UNITM, FUSED>(it, P, tiles, bars); break;
+    case 2: run_item<1, 0, NC, LAW, GUARD0, COUNT, UNITM, FUSED>(it, P, tiles, bars); break;
+    case 3: run_item<1, 1, NC, LAW, GUARD0, COUNT, UNITM, FUSED>(it, P, tiles, bars); break;
+    case 4: run_item<2, 0, NC, LAW, GUARD0, COUNT, UNITM, FUSED>(it, P, tiles, bars); break;
+    case 5: run_item<2, 1, NC, LAW, GUARD0, COUNT, UNITM, FUSED>(it, P, tiles, bars); break;
+    case 6: run_item<3, 0, NC, LAW, GUARD0, COUNT, UNITM, FUSED>(it, P, tiles, bars); break;
+    case 7: run_item<3, 1, NC, LAW, GUARD0, COUNT, UNITM, FUSED>(it, P, tiles, bars); break;
+    default: run_item<4, 0, NC, LAW, GUARD0, COUNT, UNITM, FUSED>(it, P, tiles, bars); break;
   }
 }
 
-template <int NC, int LAW, bool GUARD0, bool COUNT>
+template <int NC, int LAW, bool GUARD0, bool COUNT, bool FUSED>
 __global__ void __launch_bounds__(32) k_force(const __grid_constant__ ForceParams P, int n_items) {
   __shared__ __align__(128) float4 tiles[FSTAGES][FTILE];
   __shared__ __align__(8) unsigned long long bars[FSTAGES];
@@ -307,12 +358,12 @@ __global__ void __launch_bounds__(32) k_force(const __grid_constant__ ForceParam
   const WorkItem it = P.items[item];
   const int S = (it.sink_count + 31) / 32;
   if (LAW >= 2) {   // fit / interpolated laws: scalar form only, two code variants
-    if (S <= 2) run_item<0, 2, NC, LAW, GUARD0, COUNT, false>(it, P, tiles, bars);
-    else run_item<0, SMAX_, NC, LAW, GUARD0, COUNT, false>(it, P, tiles, bars);
+    if (S <= 2) run_item<0, 2, NC, LAW, GUARD0, COUNT, false, false>(it, P, tiles, bars);
+    else run_item<0, SMAX_, NC, LAW, GUARD0, COUNT, false, false>(it, P, tiles, bars);
     return;
   }
-  if (P.unit_mass && it.no_pseudo) dispatch_item<NC, LAW, GUARD0, COUNT, true>(S, it, P, tiles, bars);
-  else dispatch_item<NC, LAW, GUARD0, COUNT, false>(S, it, P, tiles, bars);
+  if (P.unit_mass && it.no_pseudo) dispatch_item<NC, LAW, GUARD0, COUNT, true, FUSED>(S, it, P, tiles, bars);
+  else dispatch_item<NC, LAW, GUARD0, COUNT, false, FUSED>(S, it, P, tiles, bars);
 }
 
 // ---- work items: each sink leaf is cut into equal chunks of <= 32*SMAX_ sinks ---------------------------
@@ -383,10 +434,10 @@ __global__ void k_lpt_scatter(const WorkItem *__restrict__ items, const unsigned
   out[atomicAdd(&cursor[lpt_bin(w, list_len)], 1u)] = w;
 }
 
-template <int NC, int LAW, bool GUARD0>
+template <int NC, int LAW, bool GUARD0, bool FUSED = false>
 static int launch_force(haccsr_ctx *c, const ForceParams &P, int n_items, bool count) {
-  if (count) k_force<NC, LAW, GUARD0, true><<<n_items, 32, 0, c->stream>>>(P, n_items);
-  else k_force<NC, LAW, GUARD0, false><<<n_items, 32, 0, c->stream>>>(P, n_items);
+  if (count) k_force<NC, LAW, GUARD0, true, FUSED><<<n_items, 32, 0, c->stream>>>(P, n_items);
+  else k_force<NC, LAW, GUARD0, false, FUSED><<<n_items, 32, 0, c->stream>>>(P, n_items);
   c->launches++; c->force_launches++;
   HSR_CUDA(cudaGetLastError());
   return 0;
@@ -424,8 +475,8 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   P.src4 = c->src4.p; P.pool = c->pool.p;
   P.vx = c->cur.vx; P.vy = c->cur.vy; P.vz = c->cur.vz;
   P.incut = c->d_counters + 11;
-  for (int i = 0; i < 8; ++i) P.a[i] = c->law.a[i];
-  P.rsm2 = c->law.rsm2; P.rmax2 = c->law.rmax2; P.fcoeff = fcoeff;
+  for (int i = 0; i < 8; ++i) { P.a[i] = c->law.a[i]; P.b[i] = -c->law.b[i]; }
+  P.rsm2 = c->law.rsm2; P.rmax2 = c->law.rmax2; P.smax = c->law.smax; P.fcoeff = fcoeff;
   P.unit_mass = c->unit_mass ? 1 : 0;
   P.tab_f = c->law_table.p; P.tab_r2 = c->law_table.p ? c->law_table.p + c->law.ntab : nullptr;
   P.tab_r2min = c->law.tab_r2min; P.tab_r2max = c->law.tab_r2max; P.tab_oodr2 = c->law.tab_oodr2; P.ntab = c->law.ntab;
@@ -437,7 +488,10 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   else if (c->law.kind == HACCSR_LAW_SR_INTERP) rc = guard0 ? launch_force<1, 3, true>(c, P, ni, count_in_cutoff) : launch_force<1, 3, false>(c, P, ni, count_in_cutoff);
   else {
     const bool guard = !(c->law.rsm2 > 0.0f);
-    if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false>(c, P, ni, count_in_cutoff);
+    if (c->arith == HACCSR_ARITH_FUSED) {
+      if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true, true>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false, true>(c, P, ni, count_in_cutoff);
+      else rc = guard ? launch_force<7, 0, true, true>(c, P, ni, count_in_cutoff) : launch_force<7, 0, false, true>(c, P, ni, count_in_cutoff);
+    } else if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false>(c, P, ni, count_in_cutoff);
     else rc = guard ? launch_force<7, 0, true>(c, P, ni, count_in_cutoff) : launch_force<7, 0, false>(c, P, ni, count_in_cutoff);
   }
   if (rc) return rc;

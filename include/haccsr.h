@@ -48,6 +48,18 @@ enum {
   HACCSR_LAW_NEWTON = 3
 };
 
+/* Arithmetic of the pair kernel for the polynomial law (the other laws always use the X86 order).
+ *   FUSED (default): multiply-adds contracted as in the reference's production kernel -- the QPX loop builds r2
+ *          from three fused multiply-adds (src/halo_finder/BGQStep16.c:76-86) and any FMA-capable build of nbody1
+ *          (RCBForceTree.cxx:608, gcc's default -ffp-contract=fast) contracts the same expression.  Here the chain
+ *          is seeded with rsm^2, s = fma(dz,dz, fma(dy,dy, fma(dx,dx, rsm^2))), the polynomial is evaluated in s
+ *          (re-expanded in double) and the cutoff is s < rmax^2 + rsm^2: 17 instead of 20 FMA-pipe operations a pair.
+ *          Accelerations agree with the x86-64 reference build within FP32 rounding (tests: 1e-5 of the gross sum);
+ *          pairs within one ulp of the cutoff may fall on the other side (their force is ~1e-5 of a typical pair's).
+ *   X86:   r2 = (dx*dx + dy*dy) + dz*dz unfused, in the order of the x86-64 build of the reference: the set of
+ *          pairs inside the cutoff is bit-identical to that build's. */
+enum { HACCSR_ARITH_FUSED = 0, HACCSR_ARITH_X86 = 1 };
+
 /* Mirrors RCBForceTree::printStats (RCBForceTree.cxx:460-511) plus the measurement fields of
  * SURVEY.md section 8(d). */
 typedef struct haccsr_stats {
@@ -97,6 +109,9 @@ int haccsr_set_stream(haccsr_ctx *ctx, void *cuda_stream);
 /* Replaces: the `ForceLaw *fl` and `POSVEL_T fsm` (= rmax), `POSVEL_T r` (= rsm) constructor arguments
  * (src/halo_finder/RCBForceTree.h:113-121). */
 int haccsr_set_force_law(haccsr_ctx *ctx, int kind, const float *coeffs, int ncoef, float rsm, float rmax);
+
+/* Select the pair-kernel arithmetic (HACCSR_ARITH_*); context-wide, default HACCSR_ARITH_FUSED. */
+int haccsr_set_arithmetic(haccsr_ctx *ctx, int mode);
 
 /* Copy `count` particles from host arrays into the context (H2D).
  * Replaces: handing m_xArr ... m_maskArr to the constructor (src/cpu/Particles.cxx:1317-1327). */

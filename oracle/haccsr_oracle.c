@@ -293,10 +293,26 @@ static void orc_collect_leaves(const orc_tree *t, const float *flo, const float 
   *nleaf = nl;
 }
 
+/* The polynomial sum_j a_j r2^j re-expanded in s = r2 + eps: b_k = sum_{j>=k} a_j C(j,k) (-eps)^(j-k), in double,
+ * rounded once (the same loop as haccsr_set_force_law, hacc_coral_b200/csrc/api.cu). */
+static void orc_shifted_poly(const float *a, int ncoef, float eps_f, float *b) {
+  const double eps = (double)eps_f;
+  for (int k = 0; k < ncoef; ++k) {
+    double acc = 0.0, binom = 1.0, pw = 1.0;
+    for (int j = k; j < ncoef; ++j) {
+      acc += (double)a[j] * binom * pw;
+      binom = binom * (double)(j + 1) / (double)(j + 1 - k);
+      pw *= -eps;
+    }
+    b[k] = (float)acc;
+  }
+}
+
 /* kernel_form: 0 generic nbody1 (RCBForceTree.cxx:604-618), 1 BG/Q scalar tail (BGQStep16.c:170-187 +
  * RCBForceTree.cxx:594-596), 2 = form 1 evaluated and accumulated in double (the "FP64 sum of the same
  * pair set" used to put both implementations' rounding errors on one scale), 3 = like 2 but returns in vx
- * the gross sum  sum_j |f_ij||d_ij|  (vy = vz = 0): the magnitude FP32 summation error scales with. */
+ * the gross sum  sum_j |f_ij||d_ij|  (vy = vz = 0): the magnitude FP32 summation error scales with;
+ * 4 = the fused arithmetic of libhaccsr's default mode (see below). */
 orc_result *orc_run(int64_t n, const float *x, const float *y, const float *z, const float *mass,
                     float *vx, float *vy, float *vz, /* in tree order on return: v += kick */
                     const float *boxes /* treeLo treeHi forceLo forceHi */, int law_kind, const float *coef,
@@ -384,6 +400,29 @@ orc_result *orc_run(int64_t n, const float *x, const float *y, const float *z, c
               pc += (dist2 > 0.0f && dist2 < rmax2);
             }
             vx[off + i] = ax; vy[off + i] = ay; vz[off + i] = az;
+          } else if (kernel_form == 4) {
+            /* FORM_FUSED: the contracted arithmetic of libhaccsr's HACCSR_ARITH_FUSED mode (include/haccsr.h), i.e. the
+             * multiply-add chain of the QPX loop (BGQStep16.c:76-86) seeded with rsm^2, polynomial and cutoff in
+             * s = r2 + rsm^2, accumulate-then-scale as RCBForceTree.cxx:594-596.  Pins that mode's in-cutoff pair set. */
+            float ax = 0.0f, ay = 0.0f, az = 0.0f;
+            float bb[8]; orc_shifted_poly(L.a, ncoef, L.rsm2, bb);
+            const int nc = ncoef <= 6 ? 6 : 7;
+            for (int k = ncoef; k < 8; ++k) bb[k] = 0.0f;
+            const float smax = rmax2 + L.rsm2;
+            for (int64_t j = 0; j < size; ++j) {
+              float dx = nx[j] - xi, dy = ny[j] - yi, dz = nz[j] - zi;
+              float s = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, L.rsm2)));
+              float pl = -bb[nc - 1];
+              for (int q = nc - 2; q >= 0; --q) pl = fmaf(pl, s, -bb[q]);      /* pl = -g(s) */
+              float rs = (float)(1.0 / sqrt((double)s));
+              float f = fmaf(rs * rs, rs, pl);
+              f = f * nm[j];
+              int in = s < smax;
+              if (in) { ax = fmaf(f, dx, ax); ay = fmaf(f, dy, ay); az = fmaf(f, dz, az); }
+              pc += (in && s > L.rsm2);
+            }
+            float c = fcoeff * mi;
+            vx[off + i] = fmaf(c, ax, vx[off + i]); vy[off + i] = fmaf(c, ay, vy[off + i]); vz[off + i] = fmaf(c, az, vz[off + i]);
           } else if (kernel_form == 1) {
             float ax = 0.0f, ay = 0.0f, az = 0.0f;
             const float *a = L.a;

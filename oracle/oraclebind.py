@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 LAW_POLY, LAW_NEWTON = 0, 3
-FORM_GENERIC, FORM_BGQ_TAIL, FORM_FP64, FORM_GROSS = 0, 1, 2, 3
+FORM_GENERIC, FORM_BGQ_TAIL, FORM_FP64, FORM_GROSS, FORM_FUSED = 0, 1, 2, 3, 4
 POLY5 = np.array([0.269327, -0.0750978, 0.0114808, -0.00109313, 0.0000605491, -0.00000147177],
                  dtype=np.float32)   # reference ForceLaw.cxx:109-114 == BGQStep16.c:167
 POLY6 = np.array([0.271431, -0.0783394, 0.0133122, -0.00159485, 0.000132336, -0.00000663394,

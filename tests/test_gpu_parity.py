@@ -25,8 +25,17 @@ from tests.util import RSM, THETA, accel_errors, boxes, by_id, compare_trees
 pytestmark = pytest.mark.gpu
 
 
-def gpu_run(p, b, theta, ppn, coef=H.POLY5, kind=H.LAW_SR_POLY, rsm=RSM, fcoeff=1.0, want_tree=True, count=True):
-    g = H.HaccSR(max(int(p["x"].size), 1))
+ARITHS = [pytest.param(H.ARITH_FUSED, id="fused"), pytest.param(H.ARITH_X86, id="x86")]
+
+
+def count_form(oracle, arith):
+    """Oracle kernel form that pins the in-cutoff pair set of an arithmetic mode (include/haccsr.h HACCSR_ARITH_*)."""
+    return oracle.FORM_FUSED if arith == H.ARITH_FUSED else oracle.FORM_GENERIC
+
+
+def gpu_run(p, b, theta, ppn, coef=H.POLY5, kind=H.LAW_SR_POLY, rsm=RSM, fcoeff=1.0, want_tree=True, count=True,
+            arith=H.ARITH_FUSED):
+    g = H.HaccSR(max(int(p["x"].size), 1), arith=arith)
     try:
         g.set_force_law(kind, coef, rsm, H.RMAX)
         g.upload(p)
@@ -39,20 +48,45 @@ def gpu_run(p, b, theta, ppn, coef=H.POLY5, kind=H.LAW_SR_POLY, rsm=RSM, fcoeff=
     return out, st, tree, lists
 
 
-def check_accel(out, o, o64, og, tag=""):
+def _dist(a, b):
+    return np.sqrt(sum((a[k].astype(np.float64) - b[k].astype(np.float64)) ** 2 for k in ("vx", "vy", "vz")))
+
+
+def check_accel(out, o, o64, og, tag="", of=None):
+    """out = GPU, o = the reference's x86 arithmetic (oracle FORM_GENERIC or the compiled reference itself),
+    o64 / og = FP64 sum and gross sum of the same pair set, of = oracle FORM_FUSED (fused mode only).
+
+    x86 mode: gates (i)-(iii) of the module docstring, GPU within 1.25x of the CPU's own distance to FP64.
+    Fused mode: the contracted chain rounds r2 differently, so a pair within one ulp of the cutoff can fall on the
+    other side; the polynomial laws are not zero there (|f(rmax)| rmax = 3.9e-5 for poly5), so such a
+    particle differs from the x86 build by that step -- as two builds of the reference with different contraction
+    would.  Those particles are identified on the CPU (oracle fused vs oracle generic), counted and bounded; every other
+    particle meets the same 1e-5 * G_i gate against the x86 reference, and EVERY particle meets it against the oracle's
+    restatement of the fused arithmetic.  MUFU.RSQ(s) cubed carries 3x the relative error of rsqrt(s^3), so the distance
+    to the FP64 sum is allowed 4x the CPU's instead of 1.25x (measured 3.2x; about 1e-6 of |a| in the median)."""
     a, b, c = by_id(out), by_id(o), by_id(o64)
     gross = np.maximum(by_id(og)["vx"].astype(np.float64), 1e-30)
-    d = np.sqrt(sum((a[k].astype(np.float64) - b[k].astype(np.float64)) ** 2 for k in ("vx", "vy", "vz")))
+    d = _dist(a, b)
     kicked = gross > 1e-20
     assert np.all(d[~kicked] == 0), tag
-    assert (d[kicked] / gross[kicked]).max() <= 1e-5, "%s: |da|/G max %.3e" % (tag, (d[kicked] / gross[kicked]).max())
+    ok = kicked
+    slack = 1.25
+    if of is not None:
+        f = by_id(of)
+        flip = kicked & (_dist(f, b) > 1e-5 * gross)
+        assert flip.sum() <= 2 + 1e-4 * kicked.sum(), (tag, int(flip.sum()))
+        assert (_dist(f, b)[flip]).max(initial=0.0) <= 1e-4, tag              # a couple of cutoff steps at most
+        assert (_dist(a, f)[kicked] / gross[kicked]).max() <= 1e-5, "%s: GPU vs oracle fused form" % tag
+        ok = kicked & ~flip
+        slack = 4.0
+    assert (d[ok] / gross[ok]).max() <= 1e-5, "%s: |da|/G max %.3e" % (tag, (d[ok] / gross[ok]).max())
     rel, _, _, _ = accel_errors(a, b)
     r_gpu, _, _, _ = accel_errors(a, c)
     r_cpu, _, _, _ = accel_errors(b, c)
     assert np.median(rel) <= 5e-6, tag
     assert np.quantile(rel, 0.99) <= 1e-4, tag
-    assert np.quantile(r_gpu, 0.999) <= 1.25 * np.quantile(r_cpu, 0.999) + 1e-7, tag
-    assert np.median(r_gpu) <= 1.25 * np.median(r_cpu) + 1e-8, tag
+    assert np.quantile(r_gpu, 0.999) <= slack * np.quantile(r_cpu, 0.999) + 1e-7, (tag, np.quantile(r_gpu, 0.999), np.quantile(r_cpu, 0.999))
+    assert np.median(r_gpu) <= slack * np.median(r_cpu) + 1e-8, (tag, np.median(r_gpu), np.median(r_cpu))
 
 
 CASES = [
@@ -72,13 +106,22 @@ def make(kind, n):
     return synth.zeldovich(n, z=50.0, seed=10, ghost=4), n + 8
 
 
+@pytest.mark.parametrize("arith", ARITHS)
 @pytest.mark.parametrize("kind,n,ppn,theta,poly", CASES)
-def test_kick_matches_oracle(oracle, kind, n, ppn, theta, poly):
+def test_kick_matches_oracle(oracle, kind, n, ppn, theta, poly, arith):
+    """Both arithmetic modes against the reference's x86 semantics (oracle FORM_GENERIC, itself bit-equal to the compiled
+    reference): tree and evaluated pairs exact; in-cutoff pairs exact against the oracle form restating the mode's
+    arithmetic (and, for the fused mode, within a few pairs per 10^7 of the x86 set); accelerations per check_accel."""
     p, side = make(kind, n)
     b = boxes(side)
     coef = getattr(H, poly)
-    out, st, tree, _ = gpu_run(p, b, theta, ppn, coef=coef)
+    out, st, tree, _ = gpu_run(p, b, theta, ppn, coef=coef, arith=arith)
     o = oracle.run(p, *b, RSM, theta, ppn, coef=coef)
+    incut, of = o["stats"]["pairs_incut"], None
+    if arith == H.ARITH_FUSED:
+        of = oracle.run(p, *b, RSM, theta, ppn, coef=coef, form=oracle.FORM_FUSED)
+        incut = of["stats"]["pairs_incut"]
+        assert abs(incut - o["stats"]["pairs_incut"]) <= 4 + 2e-6 * o["stats"]["pairs_incut"]
     cmp_ = compare_trees(tree, out["id"], o["tree"], o["id"])
     assert cmp_["nodes_a"] == cmp_["nodes_b"]
     for k in ("missing", "box_mismatch", "xc_mismatch", "ppm_mismatch", "leaf_flag_mismatch", "leaf_members_mismatch"):
@@ -87,10 +130,10 @@ def test_kick_matches_oracle(oracle, kind, n, ppn, theta, poly):
     assert st["nodes"] == os_["nodes"] and st["leaves"] == os_["leaves"] and st["empty_leaves"] == os_["empty_leaves"]
     assert st["max_ppn"] == os_["max_ppn"] and st["sink_leaves"] == os_["sink_leaves"] and st["max_list"] == os_["max_list"]
     assert st["pairs_evaluated"] == os_["pairs_eval"]
-    assert st["pairs_in_cutoff"] == os_["pairs_incut"]
+    assert st["pairs_in_cutoff"] == incut
     o64 = oracle.run(p, *b, RSM, theta, ppn, coef=coef, form=oracle.FORM_FP64)
     og = oracle.run(p, *b, RSM, theta, ppn, coef=coef, form=oracle.FORM_GROSS)
-    check_accel(out, o, o64, og, tag="%s n=%d ppn=%d" % (kind, n, ppn))
+    check_accel(out, o, o64, og, tag="%s n=%d ppn=%d" % (kind, n, ppn), of=of)
     # the 10 arrays come back permuted consistently (RCBForceTree.cxx:648-669): same (id -> position) map
     oi = np.argsort(out["id"])
     assert np.array_equal(out["id"][oi], np.arange(p["x"].size))
@@ -99,7 +142,8 @@ def test_kick_matches_oracle(oracle, kind, n, ppn, theta, poly):
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.npz"))))
-def test_kick_matches_golden_reference_vectors(oracle, path):
+@pytest.mark.parametrize("arith", ARITHS)
+def test_kick_matches_golden_reference_vectors(oracle, path, arith):
     """Against outputs of the compiled reference itself (tests/golden/make_golden.py)."""
     d = np.load(path)
     n = d["x"].size
@@ -109,13 +153,20 @@ def test_kick_matches_golden_reference_vectors(oracle, path):
         pytest.skip("fit / interpolated law fixtures are covered by test_fit_and_interp_laws_match_reference")
     coef = H.POLY5 if int(d["law"]) == 0 else H.POLY6
     b = boxes(side, edge)
-    out, st, _, _ = gpu_run(p, b, theta, ppn, coef=coef)
+    out, st, _, _ = gpu_run(p, b, theta, ppn, coef=coef, arith=arith)
     assert st["nodes"] == int(d["nodes"]) and st["leaves"] == int(d["leaves"]) and st["max_ppn"] == int(d["max_ppn"])
-    assert st["pairs_evaluated"] == int(d["pairs_eval"]) and st["pairs_in_cutoff"] == int(d["pairs_incut"])
+    assert st["pairs_evaluated"] == int(d["pairs_eval"])
+    if arith == H.ARITH_X86:
+        assert st["pairs_in_cutoff"] == int(d["pairs_incut"])
+    of = None
+    if arith == H.ARITH_FUSED:
+        of = oracle.run(p, *b, RSM, theta, ppn, coef=coef, form=oracle.FORM_FUSED)
+        assert abs(st["pairs_in_cutoff"] - int(d["pairs_incut"])) <= 4 + 2e-6 * int(d["pairs_incut"])
+        assert st["pairs_in_cutoff"] == of["stats"]["pairs_incut"]
     ref = {"vx": d["vx"], "vy": d["vy"], "vz": d["vz"], "id": np.arange(n)}
     o64 = oracle.run(p, *b, RSM, theta, ppn, coef=oracle.POLY5 if int(d["law"]) == 0 else oracle.POLY6, form=oracle.FORM_FP64)
     og = oracle.run(p, *b, RSM, theta, ppn, coef=oracle.POLY5 if int(d["law"]) == 0 else oracle.POLY6, form=oracle.FORM_GROSS)
-    check_accel(out, ref, o64, og, tag=os.path.basename(path))
+    check_accel(out, ref, o64, og, tag=os.path.basename(path), of=of)
 
 
 @pytest.mark.parametrize("name", ["lattice16_ppn64_fit", "clustered6k_ppn32_fit", "lattice16_ppn64_interp1024"])
@@ -181,18 +232,26 @@ def test_interaction_lists_match_oracle(oracle):
         assert sorted(want_pp) == sorted(got_pp)
 
 
+@pytest.mark.parametrize("arith", ARITHS)
 @pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 64, 65, 257])
-def test_ragged_sizes(oracle, n):
+def test_ragged_sizes(oracle, n, arith):
     rng = np.random.default_rng(100 + n)
     p = synth._pack(rng.random(n) * 8, rng.random(n) * 8, rng.random(n) * 8)
     b = boxes(8, 0.0)
-    out, st, _, _ = gpu_run(p, b, 0.5, 64)
+    out, st, _, _ = gpu_run(p, b, 0.5, 64, arith=arith)
     o = oracle.run(p, *b, RSM, 0.5, 64)
-    assert st["pairs_evaluated"] == o["stats"]["pairs_eval"] and st["pairs_in_cutoff"] == o["stats"]["pairs_incut"]
+    oc = oracle.run(p, *b, RSM, 0.5, 64, form=count_form(oracle, arith))
+    assert st["pairs_evaluated"] == o["stats"]["pairs_eval"] and st["pairs_in_cutoff"] == oc["stats"]["pairs_incut"]
     assert st["nodes"] == o["stats"]["nodes"]
     if n:
+        # a handful of particles: gate on the gross sum (the scale rounding errors have), against the oracle form of the mode
+        og = oracle.run(p, *b, RSM, 0.5, 64, form=oracle.FORM_GROSS)
+        gross = np.maximum(by_id(og)["vx"].astype(np.float64), 1e-30)
+        # (+ 1e-6 absolute: a particle whose only partners sit at the cutoff has G ~ 1e-4 while each term of f = s^-3/2 - g
+        # is ~ 0.03 and carries its own 1e-7 relative rounding)
+        assert (_dist(by_id(out), by_id(oc)) / (gross + 0.1)).max() <= 1e-5
         rel, d, nb, rms = accel_errors(by_id(out), by_id(o))
-        assert np.quantile(rel, 0.99) < 1e-4 and np.median(rel) < 5e-6
+        assert np.median(rel) < 5e-6
 
 
 def test_coincident_particles_and_oversized_leaf(oracle):
@@ -218,26 +277,29 @@ def test_no_sink_leaves_when_force_box_excludes_everything():
     assert np.all(out["vx"] == 0)
 
 
-def test_long_lists_beyond_reference_vmax(oracle):
+@pytest.mark.parametrize("arith", ARITHS)
+def test_long_lists_beyond_reference_vmax(oracle, arith):
     """theta = 0.1 on a clustered snapshot makes lists longer than the reference's VMAX = 16384
     (RCBForceTree.cxx:921, where the reference aborts); the device walk has no such limit."""
     p = synth.clustered(120000, 32.0, seed=31, n_clumps=4, frac=0.8)
     b = boxes(32)
-    out, st, _, _ = gpu_run(p, b, 0.1, 512, want_tree=False)
+    out, st, _, _ = gpu_run(p, b, 0.1, 512, want_tree=False, arith=arith)
     o = oracle.run(p, *b, RSM, 0.1, 512)
+    oc = o if arith == H.ARITH_X86 else oracle.run(p, *b, RSM, 0.1, 512, form=oracle.FORM_FUSED)
     assert st["max_list"] > 16384
-    assert st["pairs_evaluated"] == o["stats"]["pairs_eval"] and st["pairs_in_cutoff"] == o["stats"]["pairs_incut"]
+    assert st["pairs_evaluated"] == o["stats"]["pairs_eval"] and st["pairs_in_cutoff"] == oc["stats"]["pairs_incut"]
     rel, _, _, _ = accel_errors(by_id(out), by_id(o))
     assert np.median(rel) < 5e-6 and np.quantile(rel, 0.999) < 1e-4
 
 
-def test_fcoeff_and_mass_scaling(oracle):
+@pytest.mark.parametrize("arith", ARITHS)
+def test_fcoeff_and_mass_scaling(oracle, arith):
     rng = np.random.default_rng(5)
     p = synth.jitter_lattice(12, seed=4)
     p["mass"] = (0.5 + rng.random(p["x"].size)).astype(np.float32)
     p["vx"] = rng.standard_normal(p["x"].size).astype(np.float32)
     b = boxes(12, 1.0)
-    out, st, tree, _ = gpu_run(p, b, 0.5, 32, fcoeff=0.37)
+    out, st, tree, _ = gpu_run(p, b, 0.5, 32, fcoeff=0.37, arith=arith)
     o = oracle.run(p, *b, RSM, 0.5, 32, fcoeff=0.37)
     assert st["pairs_evaluated"] == o["stats"]["pairs_eval"]
     cmp_ = compare_trees(tree, out["id"], o["tree"], o["id"])

@@ -12,7 +12,7 @@
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
-struct Law { float a[6]; float rsm2, rmax2; };
+struct Law { float a[6]; float rsm2, rmax2; float b[6]; float smax; };
 
 __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -188,6 +188,65 @@ __global__ void __launch_bounds__(32) k_src2(const float4 *__restrict__ src, flo
   out[blockIdx.x * 32 + threadIdx.x] = make_float4(sx, sy, sz, 0.f);
 }
 
+// ---- V4: fused arithmetic (HACCSR_ARITH_FUSED): s-seeded FMA chain, polynomial and cutoff in s, unit masses ----
+// MODE 5: f = rsqrt(s^3) - p(s)            (17 FMA-pipe operations per pair)
+// MODE 6: f = fma(rs*rs, rs, -p(s)), rs = rsqrt(s), coefficients negated on the host   (16)
+template <int S2, int MODE>
+__device__ __forceinline__ void pair_fused(const float4 s, const float2 (&xi)[S2], const float2 (&yi)[S2], const float2 (&zi)[S2],
+                                           float2 (&ax)[S2], float2 (&ay)[S2], float2 (&az)[S2], const Law &L) {
+  const float2 sx = make_float2(s.x, s.x), sy = make_float2(s.y, s.y), sz = make_float2(s.z, s.z);
+#pragma unroll
+  for (int k = 0; k < S2; ++k) {
+    float2 dx = __fadd2_rn(sx, xi[k]), dy = __fadd2_rn(sy, yi[k]), dz = __fadd2_rn(sz, zi[k]);
+    float2 t = __ffma2_rn(dx, dx, make_float2(L.rsm2, L.rsm2));
+    t = __ffma2_rn(dy, dy, t);
+    t = __ffma2_rn(dz, dz, t);
+    float2 p = make_float2(L.b[5], L.b[5]);
+#pragma unroll
+    for (int q = 4; q >= 0; --q) p = __ffma2_rn(p, t, make_float2(L.b[q], L.b[q]));
+    float2 f;
+    if (MODE == 5) {
+      float2 t3 = __fmul2_rn(__fmul2_rn(t, t), t);
+      f = make_float2(rsqrt_ftz(t3.x), rsqrt_ftz(t3.y));
+      f = __fadd2_rn(f, make_float2(-p.x, -p.y));
+    } else {
+      float2 rs = make_float2(rsqrt_ftz(t.x), rsqrt_ftz(t.y));
+      f = __ffma2_rn(__fmul2_rn(rs, rs), rs, p);     // p holds -poly (negated coefficients)
+    }
+    if (MODE == 7) {   // cutoff as predicated scalar accumulates: no FSEL
+      if (t.x < L.smax) { ax[k].x = __fmaf_rn(f.x, dx.x, ax[k].x); ay[k].x = __fmaf_rn(f.x, dy.x, ay[k].x); az[k].x = __fmaf_rn(f.x, dz.x, az[k].x); }
+      if (t.y < L.smax) { ax[k].y = __fmaf_rn(f.y, dx.y, ax[k].y); ay[k].y = __fmaf_rn(f.y, dy.y, ay[k].y); az[k].y = __fmaf_rn(f.y, dz.y, az[k].y); }
+    } else {
+    f.x = (t.x < L.smax) ? f.x : 0.0f;
+    f.y = (t.y < L.smax) ? f.y : 0.0f;
+    ax[k] = __ffma2_rn(f, dx, ax[k]); ay[k] = __ffma2_rn(f, dy, ay[k]); az[k] = __ffma2_rn(f, dz, az[k]);
+    }
+  }
+}
+template <int S2, int MODE, int UNROLL, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_fused(const float4 *__restrict__ src, float4 *__restrict__ out, Law L, int nrep) {
+  __shared__ float4 tile[TILE];
+  for (int i = threadIdx.x; i < TILE; i += 32 * WARPS) tile[i] = src[(blockIdx.x * TILE + i) & 0xffff];
+  __syncthreads();
+  float2 xi[S2], yi[S2], zi[S2], ax[S2], ay[S2], az[S2];
+  const int tid = blockIdx.x * 32 * WARPS + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < S2; ++k) {
+    float4 a = src[(tid * 2 * S2 + 2 * k) & 0xffff];
+    float4 b = src[(tid * 2 * S2 + 2 * k + 1) & 0xffff];
+    xi[k] = make_float2(-a.x, -b.x); yi[k] = make_float2(-a.y, -b.y); zi[k] = make_float2(-a.z, -b.z);
+    ax[k] = ay[k] = az[k] = make_float2(0.f, 0.f);
+  }
+  for (int r = 0; r < nrep; ++r) {
+#pragma unroll UNROLL
+    for (int j = 0; j < TILE; ++j) pair_fused<S2, MODE>(tile[j], xi, yi, zi, ax, ay, az, L);
+  }
+  float sx = 0, sy = 0, sz = 0;
+#pragma unroll
+  for (int k = 0; k < S2; ++k) { sx += ax[k].x + ax[k].y; sy += ay[k].x + ay[k].y; sz += az[k].x + az[k].y; }
+  out[tid] = make_float4(sx, sy, sz, 0.f);
+}
+
 template <typename F>
 static void run(const char *name, F launch, int sinks_per_thread, int grid, int nrep, double peak_tflops) {
   cudaEvent_t e0, e1;
@@ -229,11 +288,24 @@ int main(int argc, char **argv) {
   CK(cudaMalloc(&out, (size_t)grid * 32 * sizeof(float4)));
   Law L = {{0.269327f, -0.0750978f, 0.0114808f, -0.00109313f, 0.0000605491f, -0.00000147177f}, 0.007f * 0.007f, 3.116326355f * 3.116326355f};
   const int nrep = 200;
+  const unsigned zero = (argc > 5) ? 1u : 0u;
 #define RUN_SCALAR(S, E) run("scalar " #E, [&](int g, int n) { k_scalar<S, E><<<g, 32>>>(src, out, L, n); }, S, grid, nrep, peak)
 #define RUN_SINK2(S2, E, U) run("sink-packed mode" #E " unroll" #U, [&](int g, int n) { k_sink2<S2, E, U><<<g, 32>>>(src, out, L, n, zero); }, 2 * S2, grid, nrep, peak)
 #define RUN_SRC2(S, E) run("source-packed " #E, [&](int g, int n) { k_src2<S, E><<<g, 32>>>(src, out, L, n); }, S, grid, nrep, peak)
+  for (int q = 0; q < 6; ++q) L.b[q] = L.a[q];
+  L.smax = L.rmax2 + L.rsm2;
+  Law Ln = L;
+  for (int q = 0; q < 6; ++q) Ln.b[q] = -L.a[q];
+#define RUN_FUSED(S2, M, U, W) run("fused mode" #M " unroll" #U " warps" #W, [&](int g, int n) { k_fused<S2, M, U, W><<<g / W, 32 * W>>>(src, out, (M >= 6) ? Ln : L, n); }, 2 * S2, grid, nrep, peak)
+  if (argc > 1 && argv[1][0] == 'f') {
+    RUN_FUSED(2, 7, 2, 1); RUN_FUSED(3, 7, 1, 1); RUN_FUSED(3, 7, 2, 1); RUN_FUSED(4, 7, 1, 1); RUN_FUSED(4, 7, 2, 1);
+    RUN_FUSED(1, 5, 4, 1); RUN_FUSED(2, 5, 2, 1); RUN_FUSED(3, 5, 1, 1); RUN_FUSED(3, 5, 2, 1); RUN_FUSED(4, 5, 1, 1); RUN_FUSED(4, 5, 2, 1);
+    RUN_FUSED(1, 6, 4, 1); RUN_FUSED(2, 6, 2, 1); RUN_FUSED(3, 6, 1, 1); RUN_FUSED(3, 6, 2, 1); RUN_FUSED(4, 6, 1, 1); RUN_FUSED(4, 6, 2, 1);
+    RUN_FUSED(3, 6, 1, 4); RUN_FUSED(4, 6, 1, 4); RUN_FUSED(2, 6, 2, 4); RUN_FUSED(3, 5, 1, 4); RUN_FUSED(4, 5, 1, 4);
+    RUN_SINK2(3, 3, 2); RUN_SINK2(4, 3, 1);
+    return 0;
+  }
   RUN_SCALAR(8, true); RUN_SCALAR(8, false);
-  const unsigned zero = (argc > 5) ? 1u : 0u;
   RUN_SINK2(1, 4, 4); RUN_SINK2(2, 4, 4); RUN_SINK2(3, 4, 2); RUN_SINK2(3, 4, 1); RUN_SINK2(4, 4, 1); RUN_SINK2(4, 4, 2);
   RUN_SINK2(1, 3, 4); RUN_SINK2(2, 3, 4); RUN_SINK2(3, 3, 2); RUN_SINK2(4, 3, 1); RUN_SINK2(4, 3, 2); RUN_SINK2(4, 3, 4); RUN_SINK2(6, 3, 1);
   RUN_SINK2(1, 0, 4); RUN_SINK2(2, 0, 4); RUN_SINK2(3, 0, 2); RUN_SINK2(4, 0, 1); RUN_SINK2(4, 0, 2); RUN_SINK2(4, 0, 4); RUN_SINK2(6, 0, 1);
