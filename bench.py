@@ -37,9 +37,24 @@ def parse():
     ap.add_argument("--np-side", type=int, default=256, help="alive particles per dimension per GPU")
     ap.add_argument("--ppn", type=int, default=512, help="leaf size (reference -N 512, run_hacc.sh:2)")
     ap.add_argument("--state", default="uniform", choices=["uniform", "clustered"])
-    ap.add_argument("--sample-side", type=int, default=56, help="cut-out side (cells) for the CPU baseline")
+    ap.add_argument("--sample-side", type=int, default=112,
+                    help="cut-out side (cells) for the CPU baseline: 112^3 cells = 1.4 M particles = about 10 s on 16 cores")
+    ap.add_argument("--arith", default="fused", choices=["fused", "x86"], help="pair-kernel arithmetic (include/haccsr.h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
+
+
+def ncu_traffic(kernel, np_side, state, arith):
+    """DRAM bytes per launch of `kernel` from a committed `ncu --set full` capture of this bench command
+    (profiles/traffic.json, written by tools/summarize_ncu.py --traffic); None when no capture matches."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        for e in json.load(f):
+            if e["kernel"] == kernel and e["np_side"] == np_side and e["state"] == state and e.get("arith", "fused") == arith:
+                return e["dram_bytes_per_launch"]
+    return None
 
 
 def peaks():
@@ -119,7 +134,7 @@ def main():
     workload = "np=%d^3 alive per GPU + %d-cell overload shell (%d^3 grid units), %s Zel'dovich snapshot, ppn=%d, theta=%.1f, poly5" % (
         args.np_side, GHOST, nglt, "z=50 near-uniform" if args.state == "uniform" else "shell-crossed clustered", args.ppn, THETA)
     config = {"workload": workload, "np_side": args.np_side, "ppn": args.ppn, "theta": THETA, "rsm": RSM,
-              "force_law": "poly5", "state": args.state, "l2": "inputs larger than L2 (no flush needed)",
+              "force_law": "poly5", "arithmetic": args.arith, "state": args.state, "l2": "inputs larger than L2 (no flush needed)",
               "parallelism": "1 sub-volume per GPU, no data-path collective"}
 
     if args.impl == "reference":
@@ -171,7 +186,7 @@ def main():
     for k, v in p.items():
         t = torch.from_numpy(v).pin_memory()
         pin[k] = t.numpy()
-    g = H.HaccSR(n, device=local)
+    g = H.HaccSR(n, device=local, arith=H.ARITH_FUSED if args.arith == "fused" else H.ARITH_X86)
     g.set_force_law(H.LAW_SR_POLY, H.POLY5, RSM, H.RMAX)
     stream = torch.cuda.current_stream()
     g.set_stream(stream.cuda_stream)
@@ -255,7 +270,7 @@ def main():
                 "ms_per_step": ms_e2e_max / e2e_steps},
         "gpu_launches": int(launches_all),
         "roofline": {"bound": "fp32", "kernel": "k_force", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp32_peak, "traffic": None, "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (%s sm_max_mhz)" % (
+                     "frac": achieved / fp32_peak, "traffic": ncu_traffic("k_force", args.np_side, args.state, args.arith), "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (%s sm_max_mhz)" % (
                          props.multi_processor_count, sm_max, pk_kind),
                      "flop_per_interaction": FLOP_PER_PAIR, "ms_per_launch": ms_force / max(force_launches, 1)},
         "roofline_build": {"bound": "hbm", "kernel": "tree build (k_cm_tile + k_left_count + k_scatter + k_gather)",

@@ -85,6 +85,7 @@ def load_library():
     lib.haccsr_resident.restype = C.c_int64
     lib.haccsr_resident.argtypes = [vp]
     lib.haccsr_get_tree.argtypes = [vp, C.c_int64, ip64, i32p, i32p, i32p, i32p, fp]
+    lib.haccsr_get_pseudo_particles.argtypes = [vp, C.c_int64, fp]
     u32p = C.POINTER(C.c_uint32)
     lib.haccsr_get_lists.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, ip64, ip64, ip64, u32p, u32p, fp]
     _LIB = lib
@@ -95,7 +96,8 @@ EXPORTS = ["haccsr_last_error", "haccsr_device_count", "haccsr_create", "haccsr_
            "haccsr_set_force_law", "haccsr_set_arithmetic", "haccsr_upload", "haccsr_download", "haccsr_host_register",
            "haccsr_host_unregister", "haccsr_kick", "haccsr_kick_host", "haccsr_stream", "haccsr_partition_in_box",
            "haccsr_fill_mass", "haccsr_subcycle", "haccsr_refresh_message_bytes", "haccsr_refresh_begin",
-           "haccsr_refresh_pack", "haccsr_refresh_append", "haccsr_resident", "haccsr_get_tree", "haccsr_get_lists"]
+           "haccsr_refresh_pack", "haccsr_refresh_append", "haccsr_resident", "haccsr_get_tree", "haccsr_get_pseudo_particles",
+           "haccsr_get_lists"]
 
 _F32 = ("x", "y", "z", "vx", "vy", "vz", "mass", "phi")
 
@@ -255,6 +257,14 @@ class HaccSR:
                                              t["cr"].ctypes.data_as(i32p), _fp(box)))
         t["xmin"], t["xmax"], t["xc"], t["ppm"] = box[:, 0:3], box[:, 3:6], box[:, 6:9], box[:, 9]
         return t
+
+    def pseudo_particles(self):
+        """(nodes, 12, 4) array of the quadrupole pseudo-particles (x, y, z, mass) of the last tdpts = 12 kick."""
+        nn = C.c_int64()
+        self._check(self.lib.haccsr_get_tree(self._h, 0, C.byref(nn), None, None, None, None, None))
+        pp = np.empty((nn.value, 12, 4), dtype=np.float32)
+        self._check(self.lib.haccsr_get_pseudo_particles(self._h, nn.value, _fp(pp)))
+        return pp
 
     def lists(self):
         nn, nr, npool = C.c_int64(), C.c_int64(), C.c_int64()

@@ -310,7 +310,7 @@ static int kick_impl(haccsr_ctx *c, int64_t count, const float tree_lo[3], const
                      const haccsr_kick_opts *opts, haccsr_stats *stats, const HostOut *ho) {
   if (!c) { set_error("null context"); return 1; }
   if (!c->law_set) { set_error("haccsr_kick: force law not set"); return 1; }
-  if (tdpts != 1) { set_error("haccsr_kick: only the monopole tree (TDPTS = 1, -R) is implemented; got %d", tdpts); return 1; }
+  if (tdpts != 1 && tdpts != 12) { set_error("haccsr_kick: tdpts must be 1 (RCBMonopoleForceTree, -R) or 12 (RCBQuadrupoleForceTree, -S); got %d", tdpts); return 1; }
   if (count < 0 || count > c->n_resident) { set_error("haccsr_kick: count %lld exceeds resident %lld", (long long)count, (long long)c->n_resident); return 1; }
   if (ppn < 1) { set_error("haccsr_kick: ppn must be >= 1"); return 1; }
   if (!tree_lo || !tree_hi || !force_lo || !force_hi) { set_error("haccsr_kick: null box"); return 1; }
@@ -324,7 +324,7 @@ static int kick_impl(haccsr_ctx *c, int64_t count, const float tree_lo[3], const
   c->launches = 0; c->force_launches = 0;
   cudaStream_t s = c->stream;
   HSR_CUDA(cudaEventRecord(c->ev[0], s));
-  HSR_TRY(build_tree(c, count, tree_lo, tree_hi, ppn));
+  HSR_TRY(build_tree(c, count, tree_lo, tree_hi, ppn, tdpts));
   HSR_CUDA(cudaEventRecord(c->ev[1], s));
   if (ho) {
     // the build has permuted all ten arrays into c->cur; everything but the velocities is final now
@@ -492,6 +492,16 @@ int haccsr_get_tree(haccsr_ctx *c, int64_t cap, int64_t *nodes, int32_t *count, 
     }
   }
   free(h);
+  return 0;
+}
+
+int haccsr_get_pseudo_particles(haccsr_ctx *c, int64_t cap_nodes, float *pp /* 48 per node */) {
+  if (!c) { set_error("null context"); return 1; }
+  if (c->tdpts != 12) { set_error("haccsr_get_pseudo_particles: the last kick was not a quadrupole (tdpts = 12) kick"); return 1; }
+  if (cap_nodes < c->n_nodes || !pp) { set_error("haccsr_get_pseudo_particles: buffer too small"); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  HSR_CUDA(cudaStreamSynchronize(c->stream));
+  HSR_CUDA(cudaMemcpy(pp, c->pp12.p, 12 * (size_t)c->n_nodes * sizeof(float4), cudaMemcpyDeviceToHost));
   return 0;
 }
 

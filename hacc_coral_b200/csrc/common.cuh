@@ -117,6 +117,8 @@ struct haccsr_ctx {
   haccsr::DevBuf<int> nidA, nidB;                   // node owning each position at the current level (-1 = final)
   haccsr::DevBuf<haccsr::Node> nodes;
   haccsr::DevBuf<haccsr::NodeAcc> acc;
+  haccsr::DevBuf<float4> pp12;                      // TDPTS = 12: the 12 pseudo-particles (x,y,z,m) of every node
+  int tdpts = 1;                                    // pseudo-particles per accepted node of the last build (1 or 12)
   haccsr::DevBuf<int> lstart, lend, lbase, nleft;   // per node: local prefixes at first / last particle, L(o_k), is_k
   haccsr::DevBuf<unsigned> tilecount, tilebase;     // per tile: left count, exclusive scan
   haccsr::DevBuf<unsigned> scratch_u32;             // maxima for the fixed-point scales etc.
@@ -161,7 +163,7 @@ struct haccsr_ctx {
 
 namespace haccsr {
 // tree_build.cu
-int build_tree(haccsr_ctx *c, int64_t n, const float lo[3], const float hi[3], int64_t ppn);
+int build_tree(haccsr_ctx *c, int64_t n, const float lo[3], const float hi[3], int64_t ppn, int tdpts);
 // walk.cu
 int build_lists(haccsr_ctx *c, const float flo[3], const float fhi[3], float theta, haccsr_stats *st);
 // force.cu

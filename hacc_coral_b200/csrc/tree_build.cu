@@ -464,6 +464,133 @@ __global__ void k_moments(Node *__restrict__ nodes, const float4 *__restrict__ s
   nodes[k].ppm = s;
 }
 
+// ---- quadrupole pseudo-particles (RCBForceTree<12>, -S): reference RCBForceTree.cxx:229-272,519-569 ----------------
+// Every node carries 12 pseudo-particles on an icosahedron of radius tdr = 0.9 * (smallest distance from the
+// centroid to a face of the tight box) about the centroid; their masses reproduce the node's monopole, dipole and
+// quadrupole (pp<12>, :536-569).  Leaves sum over their particles (:789-797), internal nodes over the pseudo-particles
+// of their children, or over a child's particles when it has <= 12 of them (:856-889).  All arithmetic is float in the
+// reference's order with explicit round-to-nearest intrinsics (the x86-64 build has no FMA); a leaf's sum over
+// particles is a fixed-shape warp reduction instead of the reference's sequential loop, so masses agree to FP32
+// rounding (~1e-6 relative), not bit for bit.  Stored as float4 (x,y,z,m): pp12[12*node + j].
+__constant__ float c_d12[3][12];   // the 12-point spherical 4-design of Hardin & Sloane, point order of :229-272
+static const float ICO_P = 0.525731112119134f, ICO_Q = 0.85065080835204f;
+static const float h_d12[3][12] = {
+    {0, 0, ICO_P, -ICO_P, ICO_Q, -ICO_Q, 0, 0, -ICO_P, ICO_P, -ICO_Q, ICO_Q},
+    {ICO_Q, ICO_Q, 0, 0, ICO_P, ICO_P, -ICO_Q, -ICO_Q, 0, 0, -ICO_P, -ICO_P},
+    {ICO_P, -ICO_P, ICO_Q, ICO_Q, 0, 0, -ICO_P, ICO_P, -ICO_Q, -ICO_Q, 0, 0}};
+
+struct PPFrame {          // the target node's design points relative to its centroid
+  float xj[12], yj[12], zj[12], rj[12];
+  bool nz[12];            // rj2 != 0 (:553)
+  float xc[3], tdr;
+};
+__device__ __forceinline__ float pp_tdr(const Node &nd) {                      // :519-523 times ppContract = 0.9
+  float m = fminf(__fsub_rn(nd.xmax[0], nd.xc[0]), fminf(__fsub_rn(nd.xmax[1], nd.xc[1]), fminf(__fsub_rn(nd.xmax[2], nd.xc[2]),
+            fminf(__fsub_rn(nd.xc[0], nd.xmin[0]), fminf(__fsub_rn(nd.xc[1], nd.xmin[1]), __fsub_rn(nd.xc[2], nd.xmin[2]))))));
+  return __fmul_rn(0.9f, m);
+}
+__device__ __forceinline__ void pp_frame(const Node &nd, PPFrame &F, float4 *out /* 12 positions, or null */) {
+  F.tdr = pp_tdr(nd);
+  F.xc[0] = nd.xc[0]; F.xc[1] = nd.xc[1]; F.xc[2] = nd.xc[2];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    const float px = __fadd_rn(__fmul_rn(F.tdr, c_d12[0][j]), nd.xc[0]);       // :525-534
+    const float py = __fadd_rn(__fmul_rn(F.tdr, c_d12[1][j]), nd.xc[1]);
+    const float pz = __fadd_rn(__fmul_rn(F.tdr, c_d12[2][j]), nd.xc[2]);
+    if (out) out[j] = make_float4(px, py, pz, 0.f);
+    F.xj[j] = __fsub_rn(px, nd.xc[0]); F.yj[j] = __fsub_rn(py, nd.xc[1]); F.zj[j] = __fsub_rn(pz, nd.xc[2]);   // :548-550
+    const float rj2 = __fadd_rn(__fadd_rn(__fmul_rn(F.xj[j], F.xj[j]), __fmul_rn(F.yj[j], F.yj[j])), __fmul_rn(F.zj[j], F.zj[j]));
+    F.nz[j] = rj2 != 0.0f;
+    F.rj[j] = __fsqrt_rn(rj2);
+  }
+}
+// ppm[j] += mass * (odr0 + odr1 + odr2) for one source (:541-566)
+__device__ __forceinline__ void pp_add(const PPFrame &F, float x, float y, float z, float mass, float (&ppm)[12]) {
+  const float K = 12.0f;
+  const float odr0 = __fdiv_rn(1.0f, K), k3 = __fdiv_rn(3.0f, K), k5 = __fdiv_rn(5.0f, K);
+  const float xi = __fsub_rn(x, F.xc[0]), yi = __fsub_rn(y, F.xc[1]), zi = __fsub_rn(z, F.xc[2]);
+  const float ri = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(xi, xi), __fmul_rn(yi, yi)), __fmul_rn(zi, zi)));
+  const float q = __fdiv_rn(ri, F.tdr);
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    float odr1 = 0.f, odr2 = 0.f;
+    if (F.nz[j]) {
+      const float dot = __fadd_rn(__fadd_rn(__fmul_rn(xi, F.xj[j]), __fmul_rn(yi, F.yj[j])), __fmul_rn(zi, F.zj[j]));
+      const float aij = __fdiv_rn(dot, __fmul_rn(ri, F.rj[j]));
+      odr1 = __fmul_rn(__fmul_rn(k3, q), aij);
+      // (5/K)*q*q*0.5*(3*aij*aij - 1): the 0.5 is a double literal, so the last product is exact in double and
+      // rounded to float once -- identical to rounding A*B in float and halving
+      const float A = __fmul_rn(__fmul_rn(k5, q), q);
+      const float B = __fsub_rn(__fmul_rn(__fmul_rn(3.0f, aij), aij), 1.0f);
+      odr2 = __fmul_rn(__fmul_rn(A, B), 0.5f);
+    }
+    ppm[j] = __fadd_rn(ppm[j], __fmul_rn(mass, __fadd_rn(__fadd_rn(odr0, odr1), odr2)));
+  }
+}
+
+// one warp per leaf: pseudo-particle masses from the leaf's particles (:789-797)
+__global__ void __launch_bounds__(256) k_pp12_leaf(const Node *__restrict__ nodes, int n_nodes, int ppn,
+                                                    const float4 *__restrict__ src4, float4 *__restrict__ pp12) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k >= n_nodes) return;
+  const Node nd = nodes[k];
+  if (nd.cl != 0 || nd.cr != 0 || nd.count <= 0) return;      // internal nodes: k_pp12_internal; empty orphans: unused
+  PPFrame F;
+  float4 pos[12];
+  pp_frame(nd, F, pos);
+  float ppm[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) ppm[j] = 0.f;
+  // count <= 12: the pseudo-particles are never used (:791); count > ppn: a degenerate split, the reference leaves the
+  // masses at zero because both children are empty (:727-729,856-889)
+  if (nd.count > 12 && nd.count <= ppn) {
+    for (int i = lane; i < nd.count; i += 32) {
+      const float4 r = __ldg(src4 + nd.offset + i);
+      pp_add(F, r.x, r.y, r.z, r.w, ppm);
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j)
+      for (int o = 16; o > 0; o >>= 1) ppm[j] = __fadd_rn(ppm[j], __shfl_xor_sync(0xffffffffu, ppm[j], o));
+  }
+  if (lane < 12) {
+    float4 v = pos[0]; float m = ppm[0];
+#pragma unroll
+    for (int j = 1; j < 12; ++j) if (lane == j) { v = pos[j]; m = ppm[j]; }
+    v.w = m;
+    pp12[12 * (size_t)k + lane] = v;
+  }
+}
+
+// one thread per internal node of one level, bottom-up: masses from the children (:856-889)
+__global__ void __launch_bounds__(128) k_pp12_internal(const Node *__restrict__ nodes, int begin, int end,
+                                                        const float4 *__restrict__ src4, float4 *__restrict__ pp12) {
+  const int k = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= end) return;
+  const Node nd = nodes[k];
+  if (nd.cl == 0 && nd.cr == 0) return;
+  PPFrame F;
+  float4 pos[12];
+  pp_frame(nd, F, pos);
+  float ppm[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) ppm[j] = 0.f;
+  const int ch[2] = {nd.cl, nd.cr};
+  for (int s = 0; s < 2; ++s) {
+    const int c = ch[s];
+    if (c <= 0) continue;
+    const int cnt = nodes[c].count, off = nodes[c].offset;
+    if (cnt <= 0) continue;
+    const float4 *srcp = (cnt <= 12) ? (src4 + off) : (pp12 + 12 * (size_t)c);
+    const int m = (cnt <= 12) ? cnt : 12;
+    for (int i = 0; i < m; ++i) {
+      const float4 r = srcp[i];
+      pp_add(F, r.x, r.y, r.z, r.w, ppm);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 12; ++j) { float4 v = pos[j]; v.w = ppm[j]; pp12[12 * (size_t)k + j] = v; }
+}
+
 // ---- permute the caller-visible arrays into tree order (the reference does this in place, :648-669) ------
 __global__ void __launch_bounds__(256) k_gather(Soa in, Soa out, const float4 *__restrict__ src4,
                                                 const unsigned *__restrict__ perm, int n) {
@@ -484,7 +611,8 @@ int scan_exclusive(haccsr_ctx *c, const unsigned *in, unsigned *out, int64_t n, 
   return 0;
 }
 
-int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3], int64_t ppn64) {
+int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3], int64_t ppn64, int tdpts) {
+  c->tdpts = tdpts;
   if (n64 >= (int64_t)INT_MAX - 2 * TILE) { set_error("too many particles for 32-bit indexing: %lld", (long long)n64); return 1; }
   const int n = (int)n64;
   const int ppn = (int)(ppn64 > INT_MAX ? INT_MAX : ppn64);
@@ -576,6 +704,22 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
       int nl = c->level_end[L] - c->level_begin[L];
       k_moments<<<(nl + 255) / 256, 256, 0, st>>>(c->nodes.p, c->src4.p, c->level_begin[L], c->level_end[L]);
       c->launches++;
+    }
+    if (tdpts == 12) {
+      static bool design_loaded[64] = {false};
+      if (!design_loaded[c->device & 63]) {
+        HSR_CUDA(cudaMemcpyToSymbolAsync(c_d12, h_d12, sizeof(h_d12), 0, cudaMemcpyHostToDevice, st));
+        design_loaded[c->device & 63] = true;
+      }
+      HSR_TRY(c->pp12.ensure(12 * (size_t)nnodes + 12));
+      k_pp12_leaf<<<(int)(((int64_t)nnodes * 32 + 255) / 256), 256, 0, st>>>(c->nodes.p, nnodes, ppn, c->src4.p, c->pp12.p);
+      c->launches++;
+      for (int L = c->n_levels - 2; L >= 0; --L) {
+        int nl = c->level_end[L] - c->level_begin[L];
+        k_pp12_internal<<<(nl + 127) / 128, 128, 0, st>>>(c->nodes.p, c->level_begin[L], c->level_end[L], c->src4.p, c->pp12.p);
+        c->launches++;
+      }
+      HSR_CUDA(cudaGetLastError());
     }
     if (c->wait_up2) { HSR_CUDA(cudaStreamWaitEvent(st, c->ev_up2, 0)); c->wait_up2 = false; }
     k_gather<<<grid_lin, 256, 0, st>>>(c->cur, c->alt, c->src4.p, c->perm.p, n);

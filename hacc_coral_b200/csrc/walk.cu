@@ -4,7 +4,7 @@
 // box (:1166-1170); its list is built by a LIFO walk from the root (:934-936) in which ancestors of the
 // sink are always opened (:947-962), any other node is accepted as a monopole if its box diagonal^2 does
 // not exceed dist2*tan^2(theta) (:965-1021) -- then dropped if its centroid is farther than rmax (:1024),
-// else appended as its single particle (count <= 1, :1033-1049) or as one pseudo-particle (:1053-1062) --
+// else appended as its own particles (count <= TDPTS, :1033-1049) or as TDPTS pseudo-particles (:1053-1062) --
 // opened leaves are appended whole (:1063-1080), children of opened internal nodes are queued only if
 // their box is within rmax of the sink's box in every dimension (:1088-1123), and the sink leaf itself
 // comes last (:1126-1139).  All acceptance arithmetic is float, evaluated in the reference's order with
@@ -30,6 +30,8 @@ struct WalkParams {
   float flo[3], fhi[3];
   float rmax, rmax2, tan_oa;
   int n_nodes;
+  int tdpts;               // pseudo-particles per accepted node: 1 (monopole) or 12 (quadrupole)
+  const float4 *pp12;      // tdpts == 12: the nodes' pseudo-particles (tree_build.cu)
 };
 
 __device__ __forceinline__ void load_node(const Node *__restrict__ nodes, int k, Node &nd) {
@@ -138,10 +140,17 @@ __global__ void __launch_bounds__(128) k_walk(const Node *__restrict__ nodes, Wa
     }
     if (!big) {
       if (dist2 > P.rmax2) continue;                                        // :1024-1029
-      if (N.count <= 1) emit_range<FILL>(e, (unsigned)N.offset, (unsigned)N.count, out);   // :1033-1049
-      else {                                                                // :1053-1062
+      if (N.count <= P.tdpts) emit_range<FILL>(e, (unsigned)N.offset, (unsigned)N.count, out);   // :1033-1049
+      else if (P.tdpts == 1) {                                              // :1053-1062
         if (FILL) pp[e.np] = make_float4(N.xc[0], N.xc[1], N.xc[2], N.ppm);
         e.np++; e.len++;
+      } else {
+        if (FILL) {
+          const float4 *q = P.pp12 + 12 * (size_t)tln;
+#pragma unroll
+          for (int j = 0; j < 12; ++j) pp[e.np + j] = __ldg(q + j);
+        }
+        e.np += 12; e.len += 12;
       }
       continue;
     }
@@ -216,6 +225,7 @@ int build_lists(haccsr_ctx *c, const float flo[3], const float fhi[3], float the
   P.rmax = c->law.rmax; P.rmax2 = c->law.rmax2;
   P.tan_oa = tanf(theta);                       // RCBForceTree.cxx:381
   P.n_nodes = nn;
+  P.tdpts = c->tdpts; P.pp12 = c->pp12.p;
   int *d_err = reinterpret_cast<int *>(c->d_counters + 15);
   HSR_CUDA(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), s));
   const int grid = (nn + 127) / 128;

@@ -119,5 +119,5 @@ void RCBForceTree<TDPTS>::printStats(double buildTime) {
   printf("\t\tbuild time: %g s\n", buildTime);
 }
 
-template class RCBForceTree<QUADRUPOLE_TDPTS>;   // constructing it aborts: the quadrupole tree is not implemented yet
+template class RCBForceTree<QUADRUPOLE_TDPTS>;
 template class RCBForceTree<MONOPOLE_TDPTS>;

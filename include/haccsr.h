@@ -135,7 +135,9 @@ int haccsr_host_unregister(void *ptr);
  * Replaces: RCBForceTree<1>::RCBForceTree(...) in full (src/halo_finder/RCBForceTree.cxx:335-450):
  *   tree_lo/tree_hi   = minLoc/maxLoc, force_lo/force_hi = minForceLoc/maxForceLoc, theta = oa, ppn = nd,
  *   fcoeff = fcoeff; only the first `count` resident particles take part (Particles.cxx:1248).
- * tdpts must be 1 (monopole, -R); the quadrupole mode (12) is not implemented and is refused.
+ * tdpts = 1: RCBMonopoleForceTree (-R), an accepted node enters the list as one pseudo-particle at its centroid;
+ * tdpts = 12: RCBQuadrupoleForceTree (-S), as 12 pseudo-particles on an icosahedron carrying its monopole, dipole and
+ * quadrupole (RCBForceTree.cxx:229-272,519-569; RCBForceTree.h:202-203).  Other values are refused.
  * stats and opts may be NULL. */
 int haccsr_kick(haccsr_ctx *ctx, int64_t count, const float tree_lo[3], const float tree_hi[3],
                 const float force_lo[3], const float force_hi[3], float theta, int64_t ppn, int tdpts,
@@ -203,6 +205,9 @@ int64_t haccsr_resident(haccsr_ctx *ctx);
  * (TreeNode, src/halo_finder/RCBForceTree.h:131-147).  Returns the node count in *nodes. */
 int haccsr_get_tree(haccsr_ctx *ctx, int64_t cap, int64_t *nodes, int32_t *count, int32_t *offset,
                     int32_t *cl, int32_t *cr, float *box10);
+/* The 12 pseudo-particles (x, y, z, mass) of every node of the last kick made with tdpts = 12: 48 floats per node
+ * (pppts<12> / pp<12>, RCBForceTree.cxx:525-569). */
+int haccsr_get_pseudo_particles(haccsr_ctx *ctx, int64_t cap_nodes, float *pp48);
 /* Interaction lists of the last kick.  For node k: ranges [range_off[k], range_off[k+1]) of
  * (start,count) pairs.  start < 2^31 indexes particles in tree order; start >= 2^31 indexes the
  * pseudo-particle pool (start - 2^31).  Query sizes first with cap_* = 0. */

@@ -12,7 +12,8 @@
  * check that this restatement reproduces the compiled reference bit-for-bit (kicked velocities, node
  * table, permutation) on seeded snapshots, and against fixtures in tests/golden/ generated from it.
  *
- * Monopole (TDPTS = 1) only.  Arithmetic is kept in the reference's order, in float, with no FMA
+ * Monopole (TDPTS = 1) and quadrupole (TDPTS = 12 pseudo-particles on an icosahedron, :229-272,519-569;
+ * selected with orc_set_tdpts).  Arithmetic is kept in the reference's order, in float, with no FMA
  * contraction (build with -ffp-contract=off), so results are comparable bit-for-bit.
  */
 #include <math.h>
@@ -22,9 +23,61 @@
 
 typedef struct {
   int64_t count, offset, cl, cr;
-  float ppm, tdr;
+  float ppm, tdr;          /* ppm: the monopole mass (TDPTS = 1) */
   float xmin[3], xmax[3], xc[3];
+  float ppm12[12];         /* pseudo-particle masses for TDPTS = 12 */
 } orc_node;
+
+/* TDPTS of the RCBForceTree<TDPTS> instantiation being restated: 1 (RCBMonopoleForceTree, -R) or
+ * 12 (RCBQuadrupoleForceTree, -S); RCBForceTree.h:202-203. */
+static int g_tdpts = 1;
+void orc_set_tdpts(int t) { g_tdpts = (t == 12) ? 12 : 1; }
+static const float g_ppc = 0.9f;   /* ppContract, the constructor's `ppc` default (RCBForceTree.h:123) */
+
+/* The 12-point spherical 4-design of Hardin & Sloane (vertices of an icosahedron) in the point order of
+ * RCBForceTree.cxx:229-272: p = 0.525731112119134, q = 0.85065080835204. */
+#define ICO_P 0.525731112119134f
+#define ICO_Q 0.85065080835204f
+static const float g_d12x[12] = { 0, 0, ICO_P, -ICO_P, ICO_Q, -ICO_Q, 0, 0, -ICO_P, ICO_P, -ICO_Q, ICO_Q };
+static const float g_d12y[12] = { ICO_Q, ICO_Q, 0, 0, ICO_P, ICO_P, -ICO_Q, -ICO_Q, 0, 0, -ICO_P, -ICO_P };
+static const float g_d12z[12] = { ICO_P, -ICO_P, ICO_Q, ICO_Q, 0, 0, -ICO_P, ICO_P, -ICO_Q, -ICO_Q, 0, 0 };
+
+/* :519-523 */
+static float orc_pptdr(const float *xmin, const float *xmax, const float *xc) {
+  return fminf(xmax[0] - xc[0], fminf(xmax[1] - xc[1], fminf(xmax[2] - xc[2], fminf(xc[0] - xmin[0],
+               fminf(xc[1] - xmin[1], xc[2] - xmin[2])))));
+}
+/* :525-534 */
+static void orc_pppts12(float tdr, const float *xc, float *ppx, float *ppy, float *ppz) {
+  for (int i = 0; i < 12; ++i) {
+    ppx[i] = tdr * g_d12x[i] + xc[0];
+    ppy[i] = tdr * g_d12y[i] + xc[1];
+    ppz[i] = tdr * g_d12z[i] + xc[2];
+  }
+}
+/* :536-569 with TDPTS = 12: monopole + dipole + quadrupole weights of `count` sources onto the 12 points.
+ * The 0.5 of :561 is a double literal: the product is formed in double and rounded to float once. */
+static void orc_pp12(int64_t count, const float *xx, const float *yy, const float *zz, const float *mass,
+                     const float *xc, const float *ppx, const float *ppy, const float *ppz, float *ppm, float tdr) {
+  float K = 12;
+  float odr0 = 1 / K;
+  for (int64_t i = 0; i < count; ++i) {
+    float xi = xx[i] - xc[0], yi = yy[i] - xc[1], zi = zz[i] - xc[2];
+    float ri = sqrtf(xi*xi + yi*yi + zi*zi);
+    for (int j = 0; j < 12; ++j) {
+      float xj = ppx[j] - xc[0], yj = ppy[j] - xc[1], zj = ppz[j] - xc[2];
+      float rj2 = xj*xj + yj*yj + zj*zj;
+      float odr1 = 0, odr2 = 0;
+      if (rj2 != 0) {
+        float rj = sqrtf(rj2);
+        float aij = (xi*xj + yi*yj + zi*zj) / (ri*rj);
+        odr1 = (3/K)*(ri/tdr)*aij;
+        odr2 = (float)((5/K)*(ri/tdr)*(ri/tdr)*0.5*(3*aij*aij - 1));
+      }
+      ppm[j] += mass[i]*(odr0 + odr1 + odr2);
+    }
+  }
+}
 
 typedef struct {
   /* inputs */
@@ -98,6 +151,16 @@ static void orc_build_node(orc_tree *t, int64_t tl, int64_t *idx) {
     /* pp<1> with the design point at the centre: ppm += mass*(1/K + 0 + 0), K = 1 (:536-569) */
     if (cnt > 1) for (int64_t i = 0; i < cnt; ++i) s += t->m[off + i] * (1.0f + 0.0f + 0.0f);
     t->node[tl].ppm = s;
+    if (g_tdpts == 12) {                                                        /* :789-797 */
+      orc_node *nd = &t->node[tl];
+      nd->tdr = g_ppc * orc_pptdr(nd->xmin, nd->xmax, nd->xc);
+      memset(nd->ppm12, 0, sizeof(nd->ppm12));
+      if (cnt > 12) {
+        float ppx[12], ppy[12], ppz[12];
+        orc_pppts12(nd->tdr, nd->xc, ppx, ppy, ppz);
+        orc_pp12(cnt, t->x + off, t->y + off, t->z + off, t->m + off, nd->xc, ppx, ppy, ppz, nd->ppm12, nd->tdr);
+      }
+    }
     return;
   }
   int64_t cl = orc_alloc2(t), cr = cl + 1;                                      /* :808-809 */
@@ -130,6 +193,25 @@ static void orc_build_node(orc_tree *t, int64_t tl, int64_t *idx) {
     }
   }
   t->node[tl].ppm = s;
+  if (g_tdpts == 12) {                                                          /* :856-889 */
+    orc_node *nd = &t->node[tl];
+    float ppx[12], ppy[12], ppz[12];
+    nd->tdr = g_ppc * orc_pptdr(nd->xmin, nd->xmax, nd->xc);
+    orc_pppts12(nd->tdr, nd->xc, ppx, ppy, ppz);
+    memset(nd->ppm12, 0, sizeof(nd->ppm12));
+    for (int side = 0; side < 2; ++side) {
+      const orc_node *ch = &t->node[side ? cr : cl];
+      if (ch->count <= 0) continue;
+      if (ch->count <= 12) {
+        int64_t oc = ch->offset;
+        orc_pp12(ch->count, t->x + oc, t->y + oc, t->z + oc, t->m + oc, nd->xc, ppx, ppy, ppz, nd->ppm12, nd->tdr);
+      } else {
+        float cx[12], cy[12], cz[12];
+        orc_pppts12(ch->tdr, ch->xc, cx, cy, cz);
+        orc_pp12(12, cx, cy, cz, ch->ppm12, nd->xc, ppx, ppy, ppz, nd->ppm12, nd->tdr);
+      }
+    }
+  }
 }
 
 /* ---- force laws --------------------------------------------------------------------------- */
@@ -214,7 +296,7 @@ static void orc_walk(const orc_tree *t, int64_t tl, const int64_t *anc, int nanc
     }
     if (!big) {
       if (dist2 > rmax2) continue;                                             /* :1024-1029 */
-      if (T[tln].count <= 1) orc_list_push(out, tln, 0);                       /* :1033-1049 */
+      if (T[tln].count <= g_tdpts) orc_list_push(out, tln, 0);                 /* :1033-1049 */
       else orc_list_push(out, tln, 1);                                         /* :1053-1062 */
       continue;
     } else if (T[tln].cr == 0 && T[tln].cl == 0) {                             /* :1063-1080 */
@@ -369,7 +451,7 @@ orc_result *orc_run(int64_t n, const float *x, const float *y, const float *z, c
       orc_walk(t, tl, anc + ancoff[li], (int)(ancoff[li + 1] - ancoff[li]), rmax, tan_oa, l, &stk, &stkcap);
       /* materialise the source list like the reference does (nx,ny,nz,nm; :1033-1080,1126-1139) */
       int64_t size = 0;
-      for (int64_t e = 0; e < l->n; ++e) size += l->pseudo[e] ? 1 : t->node[l->node[e]].count;
+      for (int64_t e = 0; e < l->n; ++e) size += l->pseudo[e] ? g_tdpts : t->node[l->node[e]].count;
       if (size > maxlist) maxlist = size;
       if (do_force) {
         if (size > ncap) {
@@ -380,7 +462,11 @@ orc_result *orc_run(int64_t n, const float *x, const float *y, const float *z, c
         int64_t s = 0;
         for (int64_t e = 0; e < l->n; ++e) {
           const orc_node *nd = &t->node[l->node[e]];
-          if (l->pseudo[e]) { nx[s] = nd->xc[0]; ny[s] = nd->xc[1]; nz[s] = nd->xc[2]; nm[s] = nd->ppm; s++; }
+          if (l->pseudo[e] && g_tdpts == 12) {                                  /* :1053-1062 */
+            orc_pppts12(nd->tdr, nd->xc, nx + s, ny + s, nz + s);
+            for (int q = 0; q < 12; ++q) nm[s + q] = nd->ppm12[q];
+            s += 12;
+          } else if (l->pseudo[e]) { nx[s] = nd->xc[0]; ny[s] = nd->xc[1]; nz[s] = nd->xc[2]; nm[s] = nd->ppm; s++; }
           else for (int64_t i = 0; i < nd->count; ++i) {
             nx[s] = t->x[nd->offset + i]; ny[s] = t->y[nd->offset + i]; nz[s] = t->z[nd->offset + i];
             nm[s] = t->m[nd->offset + i]; s++;
@@ -512,6 +598,14 @@ void orc_get_nodes(const orc_result *R, int64_t *count, int64_t *offset, int64_t
     count[i] = nd->count; offset[i] = nd->offset; cl[i] = nd->cl; cr[i] = nd->cr;
     for (int k = 0; k < 3; ++k) { box10[10*i + k] = nd->xmin[k]; box10[10*i + 3 + k] = nd->xmax[k]; box10[10*i + 6 + k] = nd->xc[k]; }
     box10[10*i + 9] = nd->ppm;
+  }
+}
+
+/* tdr and the 12 pseudo-particle masses per node (13 floats per node; TDPTS = 12 runs). */
+void orc_get_pp12(const orc_result *R, float *pp13) {
+  for (int64_t i = 0; i < R->t.nnode; ++i) {
+    pp13[13*i] = R->t.node[i].tdr;
+    for (int q = 0; q < 12; ++q) pp13[13*i + 1 + q] = R->t.node[i].ppm12[q];
   }
 }
 

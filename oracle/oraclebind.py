@@ -50,6 +50,8 @@ def _lib():
         lib.orc_get_nodes.argtypes = [C.c_void_p, ip, ip, ip, ip, fp]
         lib.orc_get_lists.argtypes = [C.c_void_p, ip, ip, ip, C.POINTER(C.c_uint8)]
         lib.orc_free.argtypes = [C.c_void_p]
+        lib.orc_set_tdpts.argtypes = [C.c_int]
+        lib.orc_get_pp12.argtypes = [C.c_void_p, fp]
         dp = C.POINTER(C.c_double)
         lib.orc_direct_sum.argtypes = [C.c_int64, fp, fp, fp, fp, C.c_int64, ip, fp, C.c_int, C.c_float,
                                        C.c_float, dp, dp, dp]
@@ -67,7 +69,7 @@ def _ip(a):
 
 
 def run(p, tree_lo, tree_hi, force_lo, force_hi, rsm, theta, ppn, fcoeff=1.0, rmax=RMAX, coef=POLY5,
-        law=LAW_POLY, form=FORM_GENERIC, do_force=True, keep_lists=False):
+        law=LAW_POLY, form=FORM_GENERIC, do_force=True, keep_lists=False, tdpts=1):
     """Build + walk + kick on particle dict `p` (keys x y z vx vy vz mass [phi id mask]).
 
     Returns dict with: particles permuted into tree order (all keys of p), 'perm', 'stats', 'tree'
@@ -79,6 +81,7 @@ def run(p, tree_lo, tree_hi, force_lo, force_hi, rsm, theta, ppn, fcoeff=1.0, rm
     boxes = np.array(list(tree_lo) + list(tree_hi) + list(force_lo) + list(force_hi), dtype=np.float32)
     coef = np.ascontiguousarray(coef, dtype=np.float32)
     st = OrcStats()
+    lib.orc_set_tdpts(int(tdpts))       # RCBForceTree<TDPTS>: 1 = monopole (-R), 12 = quadrupole (-S)
     h = lib.orc_run(n, _fp(x), _fp(y), _fp(z), _fp(m), _fp(vx), _fp(vy), _fp(vz), _fp(boxes), law,
                     _fp(coef), len(coef), rsm, float(rmax), theta, ppn, fcoeff, form, int(do_force),
                     int(keep_lists), C.byref(st))
@@ -90,6 +93,10 @@ def run(p, tree_lo, tree_hi, force_lo, force_hi, rsm, theta, ppn, fcoeff=1.0, rm
         box = np.empty((nn, 10), dtype=np.float32)
         lib.orc_get_nodes(h, _ip(tree["count"]), _ip(tree["offset"]), _ip(tree["cl"]), _ip(tree["cr"]), _fp(box))
         tree["xmin"], tree["xmax"], tree["xc"], tree["ppm"] = box[:, 0:3], box[:, 3:6], box[:, 6:9], box[:, 9]
+        if tdpts == 12:
+            pp = np.empty((nn, 13), dtype=np.float32)
+            lib.orc_get_pp12(h, _fp(pp))
+            tree["tdr"], tree["ppm12"] = pp[:, 0], pp[:, 1:]
         out = {"perm": perm, "tree": tree, "stats": {f: getattr(st, f) for f, _ in OrcStats._fields_}}
         for k, v in p.items():
             if k in ("vx", "vy", "vz"):
@@ -106,6 +113,7 @@ def run(p, tree_lo, tree_hi, force_lo, force_hi, rsm, theta, ppn, fcoeff=1.0, rm
             out["lists"] = {"sink_leaf": sink, "off": off, "node": node, "pseudo": pseudo}
     finally:
         lib.orc_free(h)
+        lib.orc_set_tdpts(1)
     return out
 
 

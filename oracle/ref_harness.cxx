@@ -80,29 +80,42 @@ private:
 struct NodeDump {
   std::vector<int64_t> count, offset, cl, cr;
   std::vector<float> box;  // 10 floats per node: xmin[3] xmax[3] xc[3] ppm0
+  std::vector<float> pp13; // TDPTS = 12 runs: tdr, ppm[12] per node
 };
 static NodeDump g_nodes;
+static int g_tdpts = 1;      // 1: RCBMonopoleForceTree (-R), 12: RCBQuadrupoleForceTree (-S), RCBForceTree.h:202-203
 
-class ProbeTree : public RCBMonopoleForceTree {
+struct ProbeBase {
+  virtual ~ProbeBase() {}
+  virtual void dump(NodeDump &d) const = 0;
+};
+
+template <int TD>
+class ProbeTreeT : public RCBForceTree<TD>, public ProbeBase {
 public:
-  ProbeTree(float *lo, float *hi, float *flo, float *fhi, int64_t n, float *x, float *y, float *z,
-            float *vx, float *vy, float *vz, float *m, float *phi, int64_t *id, uint16_t *mask,
-            float rmax, float rsm, float theta, int64_t ppn, int64_t ds, int64_t tmin, ForceLaw *fl,
-            float fcoeff)
-      : RCBMonopoleForceTree(lo, hi, flo, fhi, n, x, y, z, vx, vy, vz, m, phi, (ID_T *)id,
-                             (MASK_T *)mask, 1.0f, rmax, rsm, theta, ppn, ds, tmin, fl, fcoeff) {}
+  ProbeTreeT(float *lo, float *hi, float *flo, float *fhi, int64_t n, float *x, float *y, float *z,
+             float *vx, float *vy, float *vz, float *m, float *phi, int64_t *id, uint16_t *mask,
+             float rmax, float rsm, float theta, int64_t ppn, int64_t ds, int64_t tmin, ForceLaw *fl,
+             float fcoeff)
+      : RCBForceTree<TD>(lo, hi, flo, fhi, n, x, y, z, vx, vy, vz, m, phi, (ID_T *)id,
+                         (MASK_T *)mask, 1.0f, rmax, rsm, theta, ppn, ds, tmin, fl, fcoeff) {}
   void dump(NodeDump &d) const {
-    size_t n = tree.size();
+    size_t n = this->tree.size();
     d.count.resize(n); d.offset.resize(n); d.cl.resize(n); d.cr.resize(n); d.box.resize(10 * n);
+    d.pp13.assign(TD == 12 ? 13 * n : 0, 0.0f);
     for (size_t i = 0; i < n; ++i) {
-      d.count[i] = tree[i].count; d.offset[i] = tree[i].offset;
-      d.cl[i] = tree[i].cl; d.cr[i] = tree[i].cr;
+      d.count[i] = this->tree[i].count; d.offset[i] = this->tree[i].offset;
+      d.cl[i] = this->tree[i].cl; d.cr[i] = this->tree[i].cr;
       for (int k = 0; k < 3; ++k) {
-        d.box[10*i + k] = tree[i].xmin[k];
-        d.box[10*i + 3 + k] = tree[i].xmax[k];
-        d.box[10*i + 6 + k] = tree[i].xc[k];
+        d.box[10*i + k] = this->tree[i].xmin[k];
+        d.box[10*i + 3 + k] = this->tree[i].xmax[k];
+        d.box[10*i + 6 + k] = this->tree[i].xc[k];
       }
-      d.box[10*i + 9] = tree[i].ppm[0];
+      d.box[10*i + 9] = this->tree[i].ppm[0];
+      if (TD == 12) {
+        d.pp13[13*i] = this->tree[i].tdr;
+        for (int q = 0; q < 12; ++q) d.pp13[13*i + 1 + q] = this->tree[i].ppm[q];
+      }
     }
   }
 };
@@ -111,13 +124,18 @@ struct CtorArgs {
   float *lo, *hi, *flo, *fhi; int64_t n;
   float *x, *y, *z, *vx, *vy, *vz, *mass, *phi; int64_t *id; uint16_t *mask;
   float rmax, rsm, theta; int64_t ppn, ds, tmin; ForceLaw *fl; float fcoeff;
-  ProbeTree *out;
+  ProbeBase *out;
 };
 static void *ctor_thread(void *p) {
   CtorArgs *a = (CtorArgs *)p;
-  a->out = new ProbeTree(a->lo, a->hi, a->flo, a->fhi, a->n, a->x, a->y, a->z, a->vx, a->vy, a->vz,
-                         a->mass, a->phi, a->id, a->mask, a->rmax, a->rsm, a->theta, a->ppn, a->ds,
-                         a->tmin, a->fl, a->fcoeff);
+  if (g_tdpts == 12)
+    a->out = new ProbeTreeT<12>(a->lo, a->hi, a->flo, a->fhi, a->n, a->x, a->y, a->z, a->vx, a->vy, a->vz,
+                                a->mass, a->phi, a->id, a->mask, a->rmax, a->rsm, a->theta, a->ppn, a->ds,
+                                a->tmin, a->fl, a->fcoeff);
+  else
+    a->out = new ProbeTreeT<1>(a->lo, a->hi, a->flo, a->fhi, a->n, a->x, a->y, a->z, a->vx, a->vy, a->vz,
+                               a->mass, a->phi, a->id, a->mask, a->rmax, a->rsm, a->theta, a->ppn, a->ds,
+                               a->tmin, a->fl, a->fcoeff);
   return 0;
 }
 
@@ -136,6 +154,16 @@ struct ref_stats {
   double wall_s;            // whole constructor (build + walk + force)
   uint64_t pairs_eval, pairs_incut;  // only when count_pairs != 0
 };
+
+// Select the instantiation the next ref_rcb_kick constructs: 1 = RCBMonopoleForceTree, 12 = RCBQuadrupoleForceTree.
+void ref_set_tdpts(int t) { g_tdpts = (t == 12) ? 12 : 1; }
+// tdr + ppm[12] per node of the last ref_rcb_kick(keep_tree=1) call made with TDPTS = 12.
+int ref_tree_get_pp12(int64_t cap, float *pp13) {
+  int64_t n = (int64_t)g_nodes.count.size();
+  if (cap < n || g_nodes.pp13.size() != (size_t)(13 * n)) return 1;
+  memcpy(pp13, g_nodes.pp13.data(), 13 * n * sizeof(float));
+  return 0;
+}
 
 // rmax of the reference's FGrid (ForceLaw.cxx:32)
 float ref_rmax(void) { FGrid fg; return fg.rmax(); }
@@ -213,7 +241,7 @@ int ref_rcb_kick(int law, const float *coef, int ncoef, int count_pairs, int qui
   if (pthread_create(&th, &attr, ctor_thread, &a) != 0) return 2;
   pthread_join(th, 0);
   pthread_attr_destroy(&attr);
-  ProbeTree *t = a.out;
+  ProbeBase *t = a.out;
   double t1 = now_s();
   if (quiet) { fflush(stdout); dup2(saved, 1); close(saved); }
 

@@ -50,6 +50,8 @@ def _lib(vmax=False):
         lib.ref_tree_size.restype = C.c_int64
         ip = C.POINTER(C.c_int64)
         lib.ref_tree_get.argtypes = [C.c_int64, ip, ip, ip, ip, fp]
+        lib.ref_set_tdpts.argtypes = [C.c_int]
+        lib.ref_tree_get_pp12.argtypes = [C.c_int64, fp]
         _libs[key] = lib
     return _libs[key]
 
@@ -86,7 +88,7 @@ def force_law_eval(law, r2, rsm, coef=POLY5):
 
 
 def rcb_kick(p, tree_lo, tree_hi, force_lo, force_hi, rsm, theta, ppn, fcoeff=1.0, law=LAW_POLY5,
-             coef=POLY5, ds=2, tmin=128, count_pairs=False, keep_tree=False, vmax=False, quiet=True):
+             coef=POLY5, ds=2, tmin=128, count_pairs=False, keep_tree=False, vmax=False, quiet=True, tdpts=1):
     """Run the reference RCBMonopoleForceTree constructor on a copy of particle dict `p`
     (keys x y z vx vy vz mass phi id mask).  Returns (particles in reference tree order, stats dict,
     tree dict or None)."""
@@ -100,6 +102,7 @@ def rcb_kick(p, tree_lo, tree_hi, force_lo, force_hi, rsm, theta, ppn, fcoeff=1.
     boxes = np.array(list(tree_lo) + list(tree_hi) + list(force_lo) + list(force_hi), dtype=np.float32)
     coef = np.ascontiguousarray(coef, dtype=np.float32)
     st = RefStats()
+    lib.ref_set_tdpts(int(tdpts))       # 1: RCBMonopoleForceTree, 12: RCBQuadrupoleForceTree
     rc = lib.ref_rcb_kick(law, _fp(coef), len(coef), int(count_pairs), int(quiet), n,
                           _fp(q["x"]), _fp(q["y"]), _fp(q["z"]), _fp(q["vx"]), _fp(q["vy"]), _fp(q["vz"]),
                           _fp(q["mass"]), _fp(q["phi"]), q["id"].ctypes.data_as(C.POINTER(C.c_int64)),
@@ -117,4 +120,9 @@ def rcb_kick(p, tree_lo, tree_hi, force_lo, force_hi, rsm, theta, ppn, fcoeff=1.
                               tree["cl"].ctypes.data_as(ip), tree["cr"].ctypes.data_as(ip), _fp(box))
         assert rc == 0
         tree["xmin"], tree["xmax"], tree["xc"], tree["ppm"] = box[:, 0:3], box[:, 3:6], box[:, 6:9], box[:, 9]
+        if tdpts == 12:
+            pp = np.empty((m, 13), dtype=np.float32)
+            assert lib.ref_tree_get_pp12(m, _fp(pp)) == 0
+            tree["tdr"], tree["ppm12"] = pp[:, 0], pp[:, 1:]
+    lib.ref_set_tdpts(1)
     return q, stats, tree

@@ -27,10 +27,20 @@ CASES = {
     "lattice16_ppn64_fit": (synth.jitter_lattice(16, seed=11), 16, 64, 0.5, R.LAW_FIT, 3.2),
     "clustered6k_ppn32_fit": (synth.clustered(6000, 24.0, seed=13, n_clumps=6), 24, 32, 0.5, R.LAW_FIT, 3.2),
     "lattice16_ppn64_interp1024": (synth.jitter_lattice(16, seed=11), 16, 64, 0.5, R.LAW_INTERP, 3.2),
+    # RCBQuadrupoleForceTree (-S): 12 pseudo-particles per accepted node (7th tuple entry = TDPTS)
+    "quad_clustered6k_ppn32": (synth.clustered(6000, 24.0, seed=13, n_clumps=6), 24, 32, 0.5, R.LAW_POLY5, 3.2, 12),
+    "quad_clustered20k_ppn64_theta03": (synth.clustered(20000, 24.0, seed=15), 24, 64, 0.3, R.LAW_POLY5, 3.2, 12),
+    "quad_lattice16_ppn64": (synth.jitter_lattice(16, seed=11), 16, 64, 0.5, R.LAW_POLY5, 3.2, 12),
 }
 NINTERP = 1024
 
-for name, (p, n, ppn, theta, law, edge) in CASES.items():
+ONLY = sys.argv[1:]      # optional: fixture names to (re)generate; default all
+
+for name, case in CASES.items():
+    if ONLY and name not in ONLY:
+        continue
+    p, n, ppn, theta, law, edge = case[:6]
+    tdpts = case[6] if len(case) > 6 else 1
     lo, hi, flo, fhi = [0.0] * 3, [float(n)] * 3, [edge] * 3, [float(n) - edge] * 3
     extra = {}
     coef = R.POLY5
@@ -40,7 +50,11 @@ for name, (p, n, ppn, theta, law, edge) in CASES.items():
     if law == R.LAW_FIT:
         extra["fit"] = R.fgrid_constants()
     q, st, tree = R.rcb_kick(p, lo, hi, flo, fhi, 0.007, theta, ppn, fcoeff=1.0, law=law, coef=coef, count_pairs=True,
-                             keep_tree=True)
+                             keep_tree=True, tdpts=tdpts, vmax=(tdpts == 12))
+    if tdpts == 12:   # pseudo-particle radius and masses of every node with more than 12 particles, keyed by (offset, count)
+        big = tree["count"] > 12
+        extra.update(tdpts=12, pp_offset=tree["offset"][big], pp_count=tree["count"][big], pp_tdr=tree["tdr"][big],
+                     pp_ppm12=tree["ppm12"][big], pp_leaf=((tree["cl"] == 0) & (tree["cr"] == 0))[big])
     o = np.argsort(q["id"], kind="stable")
     out = os.path.join(HERE, "ref_%s.npz" % name)
     np.savez_compressed(out, x=p["x"], y=p["y"], z=p["z"], n=n, ppn=ppn, theta=np.float32(theta), law=law,

@@ -34,14 +34,16 @@ def count_form(oracle, arith):
 
 
 def gpu_run(p, b, theta, ppn, coef=H.POLY5, kind=H.LAW_SR_POLY, rsm=RSM, fcoeff=1.0, want_tree=True, count=True,
-            arith=H.ARITH_FUSED):
+            arith=H.ARITH_FUSED, tdpts=1):
     g = H.HaccSR(max(int(p["x"].size), 1), arith=arith)
     try:
         g.set_force_law(kind, coef, rsm, H.RMAX)
         g.upload(p)
-        st = g.kick(*b, theta, ppn, fcoeff=fcoeff, count_in_cutoff=count)
+        st = g.kick(*b, theta, ppn, fcoeff=fcoeff, count_in_cutoff=count, tdpts=tdpts)
         out = g.download()
         tree = g.tree() if want_tree else None
+        if tree is not None and tdpts == 12:
+            tree["pp12"] = g.pseudo_particles()
         lists = g.lists() if want_tree else None
     finally:
         g.close()
@@ -151,6 +153,8 @@ def test_kick_matches_golden_reference_vectors(oracle, path, arith):
     side, edge, theta, ppn = int(d["n"]), float(d["edge"]), float(d["theta"]), int(d["ppn"])
     if int(d["law"]) not in (0, 1):
         pytest.skip("fit / interpolated law fixtures are covered by test_fit_and_interp_laws_match_reference")
+    if "tdpts" in d.files:
+        pytest.skip("quadrupole fixtures are covered by test_quadrupole_matches_reference")
     coef = H.POLY5 if int(d["law"]) == 0 else H.POLY6
     b = boxes(side, edge)
     out, st, _, _ = gpu_run(p, b, theta, ppn, coef=coef, arith=arith)
@@ -196,6 +200,70 @@ def test_fit_and_interp_laws_match_reference(oracle, name):
     assert (dd[kicked] / gross[kicked]).max() <= 1e-5, (dd[kicked] / gross[kicked]).max()
     rel, _, _, _ = accel_errors(a, r)
     assert np.median(rel) <= 5e-6 and np.quantile(rel, 0.99) <= 1e-4, (np.median(rel), np.quantile(rel, 0.99))
+
+
+QUAD_CASES = [("golden", "quad_clustered6k_ppn32"), ("golden", "quad_clustered20k_ppn64_theta03"),
+              ("golden", "quad_lattice16_ppn64"), ("oracle", "clustered40k")]
+
+
+@pytest.mark.parametrize("arith", ARITHS)
+@pytest.mark.parametrize("src,name", QUAD_CASES)
+def test_quadrupole_matches_reference(oracle, src, name, arith):
+    """tdpts = 12 (RCBQuadrupoleForceTree, -S): tree, evaluated pairs and in-cutoff pairs exact; the pseudo-particles of
+    every node at the reference's positions (bit-identical: same float formula) with masses equal to FP32 rounding
+    (the leaf sums are warp reductions, the reference's are sequential); kicks per check_accel against the compiled
+    reference's outputs (golden fixtures) or the oracle restatement that reproduces it bit for bit."""
+    if src == "golden":
+        d = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_%s.npz" % name))
+        p = synth._pack(d["x"], d["y"], d["z"])
+        side, edge, theta, ppn = int(d["n"]), float(d["edge"]), float(d["theta"]), int(d["ppn"])
+    else:
+        p, side, edge, theta, ppn = synth.clustered(40000, 32.0, seed=8), 32, 3.2, 0.4, 48
+    b = boxes(side, edge)
+    out, st, tree, lists = gpu_run(p, b, theta, ppn, arith=arith, tdpts=12)
+    o = oracle.run(p, *b, RSM, theta, ppn, tdpts=12)
+    ref = o
+    if src == "golden":
+        ref = {"vx": d["vx"], "vy": d["vy"], "vz": d["vz"], "id": np.arange(p["x"].size)}
+        assert st["nodes"] == int(d["nodes"]) and st["pairs_evaluated"] == int(d["pairs_eval"])
+    cmp_ = compare_trees(tree, out["id"], o["tree"], o["id"])
+    for k in ("missing", "box_mismatch", "xc_mismatch", "leaf_flag_mismatch", "leaf_members_mismatch"):
+        assert cmp_[k] == 0, (k, cmp_)
+    assert st["pairs_evaluated"] == o["stats"]["pairs_eval"] and st["pseudo_particles"] % 12 == 0
+    assert st["pseudo_particles"] > 0 or "lattice" in name       # a uniform lattice accepts no node inside rmax
+    of = None
+    if arith == H.ARITH_FUSED:
+        of = oracle.run(p, *b, RSM, theta, ppn, tdpts=12, form=oracle.FORM_FUSED)
+        # the masses differ in the last bits, so a pseudo-particle pair sitting on the cutoff cannot flip (positions are
+        # bit-identical) -- counts are exact in both modes
+        assert st["pairs_in_cutoff"] == of["stats"]["pairs_incut"]
+    else:
+        assert st["pairs_in_cutoff"] == o["stats"]["pairs_incut"]
+    # pseudo-particles, node by node (numbering differs: match on (offset, count))
+    ot = o["tree"]
+    okey = {(int(a), int(c)): i for i, (a, c) in enumerate(zip(ot["offset"], ot["count"])) if c > 12}
+    checked = 0
+    for i, (a, c) in enumerate(zip(tree["offset"], tree["count"])):
+        if c <= 12:
+            continue
+        j = okey[(int(a), int(c))]
+        pos = ot["tdr"][j] * np.stack([oracle_design(oracle)[k] for k in range(3)], axis=1).astype(np.float32) + ot["xc"][j]
+        assert np.array_equal(tree["pp12"][i][:, :3], pos.astype(np.float32)), (i, j)
+        want = ot["ppm12"][j]
+        assert np.abs(tree["pp12"][i][:, 3] - want).max() <= 2e-5 * max(np.abs(want).max(), 1.0), (i, c)
+        checked += 1
+    assert checked > 10
+    o64 = oracle.run(p, *b, RSM, theta, ppn, tdpts=12, form=oracle.FORM_FP64)
+    og = oracle.run(p, *b, RSM, theta, ppn, tdpts=12, form=oracle.FORM_GROSS)
+    check_accel(out, ref, o64, og, tag="quad %s" % name, of=of)
+
+
+def oracle_design(oracle):
+    """The icosahedron of RCBForceTree.cxx:229-272 as float32 (x, y, z) rows."""
+    P, Q = np.float32(0.525731112119134), np.float32(0.85065080835204)
+    return np.array([[0, 0, P, -P, Q, -Q, 0, 0, -P, P, -Q, Q],
+                     [Q, Q, 0, 0, P, P, -Q, -Q, 0, 0, -P, -P],
+                     [P, -P, Q, Q, 0, 0, -P, P, -Q, -Q, 0, 0]], dtype=np.float32)
 
 
 def test_interaction_lists_match_oracle(oracle):

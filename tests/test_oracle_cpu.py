@@ -48,6 +48,48 @@ def test_oracle_matches_golden_bitwise(oracle, golden_dir, name):
     assert np.array_equal(t["offset"][leaf], d["leaf_offset"]) and np.array_equal(t["count"][leaf], d["leaf_count"])
 
 
+QUAD = ["quad_clustered6k_ppn32", "quad_clustered20k_ppn64_theta03", "quad_lattice16_ppn64"]
+
+
+@pytest.mark.parametrize("name", QUAD)
+def test_quadrupole_oracle_matches_golden_bitwise(oracle, golden_dir, name):
+    """RCBQuadrupoleForceTree (TDPTS = 12, -S; RCBForceTree.cxx:229-272,519-569,856-889): the restatement reproduces
+    the compiled reference bit for bit -- kicks, pair counts, and the radius and 12 masses of every node's
+    pseudo-particles."""
+    d, p = _load(os.path.join(golden_dir, "ref_%s.npz" % name))
+    assert int(d["tdpts"]) == 12
+    n, edge = int(d["n"]), float(d["edge"])
+    o = oracle.run(p, *boxes(n, edge), float(d["rsm"]), float(d["theta"]), int(d["ppn"]), tdpts=12)
+    v = by_id(o)
+    assert np.array_equal(v["vx"], d["vx"]) and np.array_equal(v["vy"], d["vy"]) and np.array_equal(v["vz"], d["vz"])
+    st, t = o["stats"], o["tree"]
+    assert st["nodes"] == int(d["nodes"]) and st["pairs_eval"] == int(d["pairs_eval"]) and st["pairs_incut"] == int(d["pairs_incut"])
+    big = t["count"] > 12
+    assert np.array_equal(t["offset"][big], d["pp_offset"]) and np.array_equal(t["count"][big], d["pp_count"])
+    assert np.array_equal(t["tdr"][big], d["pp_tdr"]) and np.array_equal(t["ppm12"][big], d["pp_ppm12"])
+    # the 12 masses carry the node's monopole: their sum is the node's particle count (unit masses) to rounding
+    real = (t["count"] > 12) & ~((t["cl"] == 0) & (t["cr"] == 0) & (t["count"] > int(d["ppn"])))
+    m = t["ppm12"][real].astype(np.float64)
+    assert np.all(np.abs(m.sum(axis=1) - t["count"][real]) <= 1e-4 * np.abs(m).sum(axis=1))
+
+
+def test_quadrupole_changes_the_far_field_only(oracle):
+    """Same tree and same lists as the monopole run except that an accepted node contributes 12 entries instead of 1;
+    on a clustered snapshot the two kicks differ by the (small) quadrupole correction."""
+    p = synth.clustered(20000, 24.0, seed=15)
+    b = boxes(24)
+    o1 = oracle.run(p, *b, RSM, 0.5, 64)
+    o12 = oracle.run(p, *b, RSM, 0.5, 64, tdpts=12)
+    for k in ("count", "offset", "cl", "cr", "xmin", "xmax", "xc"):
+        assert np.array_equal(o1["tree"][k], o12["tree"][k]), k
+    a, c = by_id(o1), by_id(o12)
+    d = np.sqrt(sum((a[k].astype(np.float64) - c[k]) ** 2 for k in ("vx", "vy", "vz")))
+    nrm = np.sqrt(sum(a[k].astype(np.float64) ** 2 for k in ("vx", "vy", "vz")))
+    rel = d / np.maximum(nrm, 1e-3)
+    assert (d > 0).mean() > 0.01 and np.quantile(rel, 0.99) < 0.05     # only sinks that accepted a node change, and little
+    assert o12["stats"]["pairs_eval"] > o1["stats"]["pairs_eval"]
+
+
 def test_root_leaf_is_listed_twice(oracle, golden_dir):
     """N <= ppn: the reference walks the root leaf against itself and then appends it again
     (RCBForceTree.cxx:947 `tln < tl` is false for the root), so every pair is evaluated twice."""
@@ -79,6 +121,20 @@ def test_oracle_matches_compiled_reference(oracle, kind, n, ppn, theta):
     for k in ("x", "y", "z", "vx", "vy", "vz", "id"):
         assert np.array_equal(q[k], o[k]), k      # same permutation, same kicks, bit for bit
     for k in ("count", "offset", "cl", "cr", "xmin", "xmax", "xc", "ppm"):
+        assert np.array_equal(tree[k], o["tree"][k]), k
+    assert st["pairs_eval"] == o["stats"]["pairs_eval"] and st["pairs_incut"] == o["stats"]["pairs_incut"]
+
+
+@pytest.mark.parametrize("kind,n,ppn,theta", [("clustered", 24, 64, 0.5), ("clustered", 24, 20, 0.3), ("lattice", 16, 64, 0.5)])
+def test_quadrupole_oracle_matches_compiled_reference(oracle, kind, n, ppn, theta):
+    R = _ref()
+    p = synth.jitter_lattice(n, seed=111) if kind == "lattice" else synth.clustered(9000, float(n), seed=112, n_clumps=8)
+    b = boxes(n)
+    q, st, tree = R.rcb_kick(p, *b, RSM, theta, ppn, count_pairs=True, keep_tree=True, tdpts=12, vmax=True)
+    o = oracle.run(p, *b, RSM, theta, ppn, tdpts=12)
+    for k in ("x", "y", "z", "vx", "vy", "vz", "id"):
+        assert np.array_equal(q[k], o[k]), k
+    for k in ("count", "offset", "cl", "cr", "xmin", "xmax", "xc", "tdr", "ppm12"):
         assert np.array_equal(tree[k], o["tree"][k]), k
     assert st["pairs_eval"] == o["stats"]["pairs_eval"] and st["pairs_incut"] == o["stats"]["pairs_incut"]
 
