@@ -158,6 +158,14 @@ struct haccsr_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_up2 = nullptr, ev_built = nullptr, ev_main = nullptr;
   bool wait_up2 = false;    // build_tree must wait for ev_up2 before it permutes the payload arrays
+  // haccsr_kick_host: the force kernel runs as `force_groups` launches by particle range and the velocities of each
+  // range go to the host arrays ho_v on the copy stream as soon as they are final (force.cu)
+  const void *pending_ho = nullptr;   // host output arrays whose device->host copies are not queued yet (api.cu)
+  int64_t pending_count = 0;
+  int force_groups = 1;
+  int64_t group_off[9] = {0};
+  float *ho_v[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int launches = 0, force_launches = 0;
 };
 
@@ -168,6 +176,8 @@ int build_tree(haccsr_ctx *c, int64_t n, const float lo[3], const float hi[3], i
 int build_lists(haccsr_ctx *c, const float flo[3], const float fhi[3], float theta, haccsr_stats *st);
 // force.cu
 int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *st);
+// api.cu: queue the device->host copies of the seven arrays the force kernel does not write (haccsr_kick_host)
+int issue_host_out(haccsr_ctx *c);
 // api.cu: stable two-way partition of the ten arrays by a 0/1 flag
 int compact_by_flags(haccsr_ctx *c, const unsigned *flag, unsigned *pref, int64_t n, int64_t *n_kept);
 // scan utility (tree_build.cu): exclusive scan of n unsigned values; total written to *d_total (device).

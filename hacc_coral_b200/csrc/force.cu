@@ -402,44 +402,55 @@ __global__ void k_item_fill(const Node *__restrict__ nodes, const unsigned *__re
 // kernel, where SMs run out of work, shrinks from about one average item to about one small item.  The order
 // has no effect on results: every item owns its sinks.
 static constexpr int LPT_BINS = 512;
-__device__ __forceinline__ int lpt_bin(const WorkItem &w, const unsigned *__restrict__ list_len) {
+static constexpr int MAX_GROUPS = 8;
+// Items can additionally be split into `groups` launches by particle range (group = sink_begin * groups / n): used by
+// haccsr_kick_host, which copies the velocities of a range to the host as soon as the launches up to that range have
+// finished, so only the last range's copy is exposed after the force kernel.  Inside each group the order is LPT.
+__device__ __forceinline__ int lpt_bin(const WorkItem &w, const unsigned *__restrict__ list_len, int groups, int n) {
   float work = (float)((w.sink_count + 31) / 32) * (float)list_len[w.node];
   int b = (int)(16.0f * __log2f(work + 1.0f));
   b = b < 0 ? 0 : (b > LPT_BINS - 1 ? LPT_BINS - 1 : b);
-  return LPT_BINS - 1 - b;       // heavy items first
+  int g = (int)(((long long)w.sink_begin * groups) / (n > 0 ? n : 1));
+  g = g < 0 ? 0 : (g > groups - 1 ? groups - 1 : g);
+  return g * LPT_BINS + (LPT_BINS - 1 - b);       // heavy items first
 }
-__global__ void k_lpt_hist(const WorkItem *__restrict__ items, const unsigned *__restrict__ list_len, int n,
-                           unsigned *__restrict__ hist) {
+__global__ void k_lpt_hist(const WorkItem *__restrict__ items, const unsigned *__restrict__ list_len, int n, int groups,
+                           int n_part, unsigned *__restrict__ hist) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(&hist[lpt_bin(items[i], list_len)], 1u);
+  if (i < n) atomicAdd(&hist[lpt_bin(items[i], list_len, groups, n_part)], 1u);
 }
-__global__ void __launch_bounds__(LPT_BINS) k_lpt_scan(unsigned *__restrict__ hist) {   // hist -> exclusive offsets, in place
-  __shared__ unsigned s[LPT_BINS];
-  const int t = threadIdx.x;
-  s[t] = hist[t];
-  __syncthreads();
-  for (int o = 1; o < LPT_BINS; o <<= 1) {
-    unsigned v = (t >= o) ? s[t - o] : 0u;
-    __syncthreads();
-    s[t] += v;
-    __syncthreads();
-  }
-  hist[t] = s[t] - hist[t];
-}
-__global__ void k_lpt_scatter(const WorkItem *__restrict__ items, const unsigned *__restrict__ list_len, int n,
-                              unsigned *__restrict__ cursor, WorkItem *__restrict__ out) {
+__global__ void k_lpt_scatter(const WorkItem *__restrict__ items, const unsigned *__restrict__ list_len, int n, int groups,
+                              int n_part, unsigned *__restrict__ cursor, WorkItem *__restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   WorkItem w = items[i];
-  out[atomicAdd(&cursor[lpt_bin(w, list_len)], 1u)] = w;
+  out[atomicAdd(&cursor[lpt_bin(w, list_len, groups, n_part)], 1u)] = w;
 }
 
 template <int NC, int LAW, bool GUARD0, bool FUSED = false>
-static int launch_force(haccsr_ctx *c, const ForceParams &P, int n_items, bool count) {
-  if (count) k_force<NC, LAW, GUARD0, true, FUSED><<<n_items, 32, 0, c->stream>>>(P, n_items);
-  else k_force<NC, LAW, GUARD0, false, FUSED><<<n_items, 32, 0, c->stream>>>(P, n_items);
-  c->launches++; c->force_launches++;
-  HSR_CUDA(cudaGetLastError());
+static int launch_force(haccsr_ctx *c, const ForceParams &P0, int n_items, bool count) {
+  // one launch per group of items (a single group unless haccsr_kick_host asked for range-wise velocity copies)
+  const int groups = c->force_groups;
+  for (int g = 0; g < groups; ++g) {
+    const int b = groups > 1 ? (int)c->group_off[g] : 0, e = groups > 1 ? (int)c->group_off[g + 1] : n_items;
+    if (e > b) {
+      ForceParams P = P0;
+      P.items = P0.items + b;
+      if (count) k_force<NC, LAW, GUARD0, true, FUSED><<<e - b, 32, 0, c->stream>>>(P, e - b);
+      else k_force<NC, LAW, GUARD0, false, FUSED><<<e - b, 32, 0, c->stream>>>(P, e - b);
+      c->launches++; c->force_launches++;
+      HSR_CUDA(cudaGetLastError());
+    }
+    if (groups > 1 && c->ho_v[0]) {
+      // velocities of particles [lo, hi) are final once every launch up to this one is done
+      const int64_t n = c->n_tree, lo = n * g / groups, hi = n * (g + 1) / groups;
+      HSR_CUDA(cudaEventRecord(c->ev_grp[g], c->stream));
+      HSR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_grp[g], 0));
+      float *dv[3] = {c->cur.vx, c->cur.vy, c->cur.vz};
+      for (int q = 0; q < 3; ++q)
+        HSR_CUDA(cudaMemcpyAsync(c->ho_v[q] + lo, dv[q] + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+  }
   return 0;
 }
 
@@ -461,13 +472,25 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   c->launches++;
   {
     const int ni = (int)c->n_items;
-    HSR_TRY(c->items_sorted.ensure((size_t)c->n_items)); HSR_TRY(c->lpt_hist.ensure(LPT_BINS));
-    HSR_CUDA(cudaMemsetAsync(c->lpt_hist.p, 0, LPT_BINS * sizeof(unsigned), s));
-    k_lpt_hist<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, c->lpt_hist.p);
-    k_lpt_scan<<<1, LPT_BINS, 0, s>>>(c->lpt_hist.p);
-    k_lpt_scatter<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, c->lpt_hist.p, c->items_sorted.p);
-    c->launches += 3;
+    const int groups = c->force_groups, nb = groups * LPT_BINS, npart = (int)c->n_tree;
+    HSR_TRY(c->items_sorted.ensure((size_t)c->n_items)); HSR_TRY(c->lpt_hist.ensure(2 * (size_t)MAX_GROUPS * LPT_BINS));
+    unsigned *hist = c->lpt_hist.p, *cursor = c->lpt_hist.p + MAX_GROUPS * LPT_BINS;
+    HSR_CUDA(cudaMemsetAsync(hist, 0, nb * sizeof(unsigned), s));
+    k_lpt_hist<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, groups, npart, hist);
+    c->launches++;
+    HSR_TRY(scan_exclusive(c, hist, cursor, nb, nullptr));
+    if (groups > 1) {   // first item of every group, for the launch configuration
+      HSR_CUDA(cudaMemcpy2DAsync(c->h_counters + 16, sizeof(int64_t), cursor, LPT_BINS * sizeof(unsigned), sizeof(unsigned),
+                                 groups, cudaMemcpyDeviceToHost, s));
+    }
+    k_lpt_scatter<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, groups, npart, cursor, c->items_sorted.p);
+    c->launches++;
     HSR_CUDA(cudaGetLastError());
+    if (groups > 1) {
+      HSR_CUDA(cudaStreamSynchronize(s));
+      for (int g = 0; g < groups; ++g) c->group_off[g] = (int64_t)(uint32_t)(c->h_counters[16 + g] & 0xffffffffll);
+      c->group_off[groups] = ni;
+    }
   }
 
   ForceParams P;
@@ -482,6 +505,7 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   P.tab_r2min = c->law.tab_r2min; P.tab_r2max = c->law.tab_r2max; P.tab_oodr2 = c->law.tab_oodr2; P.ntab = c->law.ntab;
   const int ni = (int)c->n_items;
   int rc;
+  HSR_TRY(issue_host_out(c));     // haccsr_kick_host: all read-backs are done, the large copies can go now
   const bool guard0 = !(c->law.rsm2 > 0.0f);
   if (c->law.kind == HACCSR_LAW_NEWTON) rc = launch_force<1, 1, true>(c, P, ni, count_in_cutoff);
   else if (c->law.kind == HACCSR_LAW_SR_FIT) rc = guard0 ? launch_force<1, 2, true>(c, P, ni, count_in_cutoff) : launch_force<1, 2, false>(c, P, ni, count_in_cutoff);

@@ -473,6 +473,26 @@ def test_kick_host_equals_upload_kick_download():
     g.close()
 
 
+def test_kick_host_grouped_force_launches_bitwise():
+    """Above 2^20 particles haccsr_kick_host runs the force kernel as four launches by particle range and copies each
+    range's velocities out while the next one is computed: same bits as upload + kick + download."""
+    p = synth.zeldovich(104, z=50.0, seed=33, ghost=0)       # 1.12 M particles
+    rng = np.random.default_rng(2)
+    for k in ("vx", "vy", "vz"):
+        p[k] = rng.standard_normal(p["x"].size).astype(np.float32)
+    b = boxes(104)
+    ref, st, _, _ = gpu_run(p, b, 0.5, 256, fcoeff=0.5, want_tree=False, count=False)
+    g = H.HaccSR(p["x"].size)
+    g.set_force_law(H.LAW_SR_POLY, H.POLY5, RSM, H.RMAX)
+    q = {k: np.ascontiguousarray(v).copy() for k, v in p.items()}
+    s1 = g.kick_host(q, *b, 0.5, 256, fcoeff=0.5)
+    g.close()
+    assert s1["force_launches"] == 4 and st["force_launches"] == 1
+    assert s1["pairs_evaluated"] == st["pairs_evaluated"]
+    for k in ref:
+        assert np.array_equal(q[k], ref[k]), k
+
+
 def test_subcycle_matches_reference_emulation(oracle):
     """haccsr_subcycle (device-resident Particles::subCycle, reference src/cpu/Particles.cxx:1176-1201) against the
     same loop run on the host with the oracle as the kick: nsub x [map1, out-of-box tail move, mass = 1, tree kick on
