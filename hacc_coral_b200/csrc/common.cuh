@@ -121,6 +121,7 @@ struct haccsr_ctx {
   int tdpts = 1;                                    // pseudo-particles per accepted node of the last build (1 or 12)
   haccsr::DevBuf<int> lstart, lend, lbase, nleft;   // per node: local prefixes at first / last particle, L(o_k), is_k
   haccsr::DevBuf<unsigned> tilecount, tilebase;     // per tile: left count, exclusive scan
+  haccsr::DevBuf<unsigned> split_flag, split_rank;  // per node of the current level: splits (0/1), exclusive scan
   haccsr::DevBuf<unsigned> scratch_u32;             // maxima for the fixed-point scales etc.
   haccsr::LevelInfo *h_level = nullptr;             // pinned
   haccsr::LevelInfo *d_level = nullptr;

@@ -260,71 +260,70 @@ __global__ void __launch_bounds__(TPB) k_cm_tile(const float4 *__restrict__ rec,
 }
 
 // ---- pass B: finalize the nodes of one level, decide splits, allocate children breadth-first ----------
-__global__ void __launch_bounds__(1024) k_level_finalize(Node *__restrict__ nodes, NodeAcc *__restrict__ acc,
-                                                         int begin, int end, int next_base, int max_nodes,
-                                                         int ppn, const float *__restrict__ scales,
-                                                         LevelInfo *__restrict__ info) {
-  __shared__ int s_w[34];
-  __shared__ int s_err;
-  if (threadIdx.x == 0) s_err = 0;
-  int running = 0;
+// Three launches so that a level of 65 k nodes is as parallel as a level of one: (a) per node: box, centroid, split
+// decision; (b) k_scan over the split flags; (c) per split node: children at next_base + 2 * rank, so the numbering is
+// breadth-first and deterministic (parent index < child index, as the reference guarantees at :808-809).
+__global__ void __launch_bounds__(256) k_level_decide(Node *__restrict__ nodes, const NodeAcc *__restrict__ acc,
+                                                       int begin, int end, int ppn, const float *__restrict__ scales,
+                                                       unsigned *__restrict__ flags, LevelInfo *__restrict__ info) {
+  const int k = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == begin) info->error = 0;
+  if (k >= end) return;
   const double undo = ldexp(1.0, (int)scales[2]);
-  for (int b = begin; b < end; b += blockDim.x) {
-    int k = b + threadIdx.x;
-    bool valid = k < end;
-    int split = 0, d = -1;
-    Node nd;
-    if (valid) {
-      nd = nodes[k];
-      if (nd.count > 0) {
-        NodeAcc a = acc[k];
-        for (int q = 0; q < 3; ++q) { nd.xmin[q] = dec_f(a.umin[q]); nd.xmax[q] = dec_f(a.umax[q]); }
-        double sw = to_double128(a.lo[3], a.hi[3]);
-        for (int q = 0; q < 3; ++q) {
-          double sxq = to_double128(a.lo[q], a.hi[q]);
-          nd.xc[q] = (float)((sxq / sw) * undo);                       // BGQCM.c:209-211
-        }
-        if (nd.count > ppn) {                                          // RCBForceTree.cxx:788
-          float l0 = __fsub_rn(nd.xmax[0], nd.xmin[0]), l1 = __fsub_rn(nd.xmax[1], nd.xmin[1]),
-                l2 = __fsub_rn(nd.xmax[2], nd.xmin[2]);
-          d = (l0 > l1 && l0 > l2) ? 0 : ((l1 > l2) ? 1 : 2);          // :844-852
-          split = 1;
-        } else {
-          // leaf monopole: sum of masses (pp<1>, :536-569); unused when count <= 1 (:788-797)
-          nd.ppm = (nd.count > 1) ? (float)(sw / (double)scales[1]) : 0.f;
-        }
-      }
-      nd.split = split ? d : -1;
+  Node nd = nodes[k];
+  int split = 0, d = -1;
+  if (nd.count > 0) {
+    const NodeAcc a = acc[k];
+    for (int q = 0; q < 3; ++q) { nd.xmin[q] = dec_f(a.umin[q]); nd.xmax[q] = dec_f(a.umax[q]); }
+    const double sw = to_double128(a.lo[3], a.hi[3]);
+    for (int q = 0; q < 3; ++q) {
+      const double sxq = to_double128(a.lo[q], a.hi[q]);
+      nd.xc[q] = (float)((sxq / sw) * undo);                       // BGQCM.c:209-211
     }
-    int total;
-    int rank = block_excl_scan(split, s_w, &total);
-    if (valid) {
-      if (split) {
-        int cl = next_base + 2 * (running + rank);
-        if (cl + 1 >= max_nodes) { s_err = 1; nd.split = -1; }
-        else {
-          nd.cl = cl; nd.cr = cl + 1;     // provisional; cleared by k_set_children on a degenerate split
-          Node c;
-          c.count = 0; c.offset = 0; c.cl = 0; c.cr = 0; c.ppm = 0.f; c.parent = k; c.split = -1;
-          for (int q = 0; q < 3; ++q) { c.xmin[q] = nd.xmin[q]; c.xmax[q] = nd.xmax[q]; c.xc[q] = 0.f; }
-          Node l = c, r = c;
-          l.xmax[d] = nd.xc[d]; r.xmin[d] = nd.xc[d];                  // :747,763
-          nodes[cl] = l; nodes[cl + 1] = r;
-          NodeAcc z;
-          for (int q = 0; q < 3; ++q) { z.umin[q] = 0xffffffffu; z.umax[q] = 0u; }
-          for (int q = 0; q < 4; ++q) { z.lo[q] = 0; z.hi[q] = 0; }
-          acc[cl] = z; acc[cl + 1] = z;
-        }
-      }
-      nodes[k] = nd;
+    if (nd.count > ppn) {                                          // RCBForceTree.cxx:788
+      const float l0 = __fsub_rn(nd.xmax[0], nd.xmin[0]), l1 = __fsub_rn(nd.xmax[1], nd.xmin[1]),
+                  l2 = __fsub_rn(nd.xmax[2], nd.xmin[2]);
+      d = (l0 > l1 && l0 > l2) ? 0 : ((l1 > l2) ? 1 : 2);          // :844-852
+      split = 1;
+    } else {
+      // leaf monopole: sum of masses (pp<1>, :536-569); unused when count <= 1 (:788-797)
+      nd.ppm = (nd.count > 1) ? (float)(sw / (double)scales[1]) : 0.f;
     }
-    running += total;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int ns = s_err ? 0 : running;
-    info->begin = next_base; info->end = next_base + 2 * ns; info->nsplit = ns; info->error = s_err;
+  nd.split = split ? d : -1;
+  nodes[k] = nd;
+  flags[k - begin] = (unsigned)split;
+}
+
+__global__ void __launch_bounds__(256) k_level_children(Node *__restrict__ nodes, NodeAcc *__restrict__ acc, int begin,
+                                                         int end, int next_base, int max_nodes,
+                                                         const unsigned *__restrict__ flags,
+                                                         const unsigned *__restrict__ ranks,
+                                                         const unsigned long long *__restrict__ d_total,
+                                                         LevelInfo *__restrict__ info) {
+  const int k = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  const int ns = (int)*d_total;
+  const bool overflow = next_base + 2 * ns >= max_nodes;      // the last child index must stay below max_nodes
+  if (k == begin) {
+    info->begin = next_base; info->end = next_base + (overflow ? 0 : 2 * ns); info->nsplit = overflow ? 0 : ns;
+    info->error = overflow ? 1 : 0;
   }
+  if (k >= end || !flags[k - begin]) return;
+  if (overflow) { nodes[k].split = -1; return; }
+  Node nd = nodes[k];
+  const int d = nd.split;
+  const int cl = next_base + 2 * (int)ranks[k - begin];
+  nodes[k].cl = cl; nodes[k].cr = cl + 1;     // provisional; cleared by k_set_children on a degenerate split
+  Node c;
+  c.count = 0; c.offset = 0; c.cl = 0; c.cr = 0; c.ppm = 0.f; c.parent = k; c.split = -1;
+  for (int q = 0; q < 3; ++q) { c.xmin[q] = nd.xmin[q]; c.xmax[q] = nd.xmax[q]; c.xc[q] = 0.f; }
+  Node l = c, r = c;
+  l.xmax[d] = nd.xc[d]; r.xmin[d] = nd.xc[d];                  // :747,763
+  nodes[cl] = l; nodes[cl + 1] = r;
+  NodeAcc z;
+  for (int q = 0; q < 3; ++q) { z.umin[q] = 0xffffffffu; z.umax[q] = 0u; }
+  for (int q = 0; q < 4; ++q) { z.lo[q] = 0; z.hi[q] = 0; }
+  acc[cl] = z; acc[cl + 1] = z;
 }
 
 // ---- shared by C1 and C3: left flags of a tile and their exclusive prefix in particle order --------------
@@ -333,27 +332,44 @@ struct ItemInfo { int nd, sp, flag, excl; };
 __device__ __forceinline__ int tile_flags_scan(const float4 *__restrict__ rec, const int *__restrict__ nid,
                                                const Node *__restrict__ nodes, int n, int base, ItemInfo it[IPT],
                                                float4 r[IPT], bool load_rec, int *s_w) {
-  const int t = threadIdx.x;
-  int carry = 0;
+  // Particle i = base + j*TPB + t: in particle order the tile is IPT rows of TPB/32 warps.  One ballot per (row, warp)
+  // gives the left count of 32 consecutive particles; the IPT*TPB/32 = 32 counts are scanned by one warp -- a single
+  // barrier pair instead of IPT block-wide scans.
+  static_assert(IPT * (TPB / 32) == 32, "one warp scans the per-(row, warp) counts");
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  unsigned bal[IPT];
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
     int i = base + j * TPB + t;
     int nd = (i < n) ? nid[i] : -1;
     int sp = -1, flag = 0;
     if (nd >= 0) {
-      sp = nodes[nd].split;
+      sp = __ldg(&nodes[nd].split);
       if (load_rec) r[j] = rec[i];
       if (sp >= 0) {
         float key = load_rec ? comp(r[j], sp) : reinterpret_cast<const float *>(rec)[4 * (size_t)i + sp];
-        flag = key < nodes[nd].xc[sp];                                 // RCBForceTree.cxx:640, pivot :720
+        flag = key < __ldg(&nodes[nd].xc[sp]);                         // RCBForceTree.cxx:640, pivot :720
       }
     }
-    int total;
-    int e = block_excl_scan(flag, s_w, &total);
-    it[j].nd = nd; it[j].sp = sp; it[j].flag = flag; it[j].excl = carry + e;
-    carry += total;
+    bal[j] = __ballot_sync(0xffffffffu, flag);
+    it[j].nd = nd; it[j].sp = sp; it[j].flag = flag;
+    if (lane == 0) s_w[j * (TPB / 32) + w] = __popc(bal[j]);
   }
-  return carry;
+  __syncthreads();
+  if (w == 0) {
+    int x = s_w[lane], inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    s_w[lane] = inc - x;
+    if (lane == 31) s_w[32] = inc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) it[j].excl = s_w[j * (TPB / 32) + w] + __popc(bal[j] & ((1u << lane) - 1u));
+  return s_w[32];
 }
 
 __global__ void __launch_bounds__(TPB) k_left_count(const float4 *__restrict__ rec, const int *__restrict__ nid,
@@ -665,8 +681,15 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
       if (level >= 127) { set_error("tree deeper than 127 levels"); return 1; }
       c->level_begin[level] = begin; c->level_end[level] = end;
       k_cm_tile<<<ntiles, TPB, 0, st>>>(rec, nid, n, c->acc.p, scales);
-      k_level_finalize<<<1, 1024, 0, st>>>(c->nodes.p, c->acc.p, begin, end, nnodes, max_nodes, ppn, scales, c->d_level);
-      c->launches += 2;
+      {
+        const int nl = end - begin, gb = (nl + 255) / 256;
+        HSR_TRY(c->split_flag.ensure((size_t)nl + 1)); HSR_TRY(c->split_rank.ensure((size_t)nl + 1));
+        k_level_decide<<<gb, 256, 0, st>>>(c->nodes.p, c->acc.p, begin, end, ppn, scales, c->split_flag.p, c->d_level);
+        HSR_TRY(scan_exclusive(c, c->split_flag.p, c->split_rank.p, nl, c->d_counters + 13));
+        k_level_children<<<gb, 256, 0, st>>>(c->nodes.p, c->acc.p, begin, end, nnodes, max_nodes, c->split_flag.p,
+                                             c->split_rank.p, c->d_counters + 13, c->d_level);
+      }
+      c->launches += 3;
       HSR_CUDA(cudaMemcpyAsync(c->h_level, c->d_level, sizeof(LevelInfo), cudaMemcpyDeviceToHost, st));
       HSR_CUDA(cudaStreamSynchronize(st));
       LevelInfo li = *c->h_level;

@@ -16,6 +16,7 @@ struct Shared {
   haccsr_ctx *ctx = nullptr;
   int64_t cap = 0;
   int device = -1;
+  int arith = -1;     // HACCSR_ARITH_*; -1 = $HACCSR_ARITH ("x86" / "fused") or the library default
 };
 Shared &shared() { static Shared s; return s; }
 
@@ -46,6 +47,7 @@ haccsr_ctx *context_for(int64_t count) {
 }  // namespace
 
 void haccsr_facade_set_device(int device) { shared().device = device; }
+void haccsr_facade_set_arithmetic(int mode) { shared().arith = mode; }
 
 void haccsr_facade_release() {
   Shared &s = shared();
@@ -98,6 +100,9 @@ RCBForceTree<TDPTS>::RCBForceTree(POSVEL_T *minLoc, POSVEL_T *maxLoc, POSVEL_T *
   int ncoef = d.ncoef;
   if (d.kind == HACCSR_LAW_SR_INTERP) { coef = d.table.data(); ncoef = (int)d.table.size(); }
   if (haccsr_set_force_law(ctx, d.kind, coef, ncoef, rsm, fsm) != 0) die("haccsr_set_force_law");
+  int arith = s.arith;
+  if (arith < 0) { const char *e = getenv("HACCSR_ARITH"); arith = (e && !strcmp(e, "x86")) ? HACCSR_ARITH_X86 : HACCSR_ARITH_FUSED; }
+  if (haccsr_set_arithmetic(ctx, arith) != 0) die("haccsr_set_arithmetic");
 
   // upload -> tree build, lists, force kernel, kick -> download, transfers overlapped with the kernels
   if (haccsr_kick_host(ctx, count, xLoc, yLoc, zLoc, xVel, yVel, zVel, mass, phiLoc, idLoc, maskLoc, minLoc, maxLoc,

@@ -70,6 +70,9 @@ typedef RCBForceTree<MONOPOLE_TDPTS> RCBMonopoleForceTree;
 // ---- optional extras of the facade (not in the reference) -----------------------------------------------
 // Device used by the facade's shared context (default: $HACCSR_DEVICE or 0); call before the first tree.
 void haccsr_facade_set_device(int device);
+// Pair-kernel arithmetic of the following trees (HACCSR_ARITH_FUSED / HACCSR_ARITH_X86, include/haccsr.h);
+// default: $HACCSR_ARITH ("fused" or "x86"), else the library default (fused).
+void haccsr_facade_set_arithmetic(int mode);
 // Release the facade's shared context (device memory is otherwise kept between constructor calls, which is
 // what bigchunk does for the reference's node pool, bigchunk.h:49-139).
 void haccsr_facade_release();

@@ -5,7 +5,8 @@
 // A random sphere of nSphere unit-mass particles plus one test particle; the tree constructor kicks every
 // particle; the kick of the test particle is compared with the direct O(N) sum evaluated on the host with the
 // SAME ForceLaw object (fl->f_over_r), for the force laws and tree parameters given on the command line:
-//   facade_test <law: fit|poly|interp|newton> <theta> <ppn> <nSphere> <trials> <tolerance>
+//   facade_test <law: fit|poly|interp|newton> <theta> <ppn> <nSphere> <trials> <tolerance> [quad]
+// (`quad` builds RCBQuadrupoleForceTree, the reference's -S, instead of RCBMonopoleForceTree)
 // Exit status 0 = every trial within tolerance.
 #include <math.h>
 #include <stdio.h>
@@ -20,6 +21,7 @@ int main(int argc, char **argv) {
   const float theta = atof(argv[2]);
   const int ppn = atoi(argv[3]), nSphere = atoi(argv[4]), trials = atoi(argv[5]);
   const double tol = atof(argv[6]);
+  const bool quad = argc > 7 && !strcmp(argv[7], "quad");
   const float L = 20.0f, rSphere = 4.0f, rsm = 0.1f;      // ForceTreeTest.cxx:77 uses rsm = 0.1
 
   FGrid fg;
@@ -55,9 +57,15 @@ int main(int argc, char **argv) {
     for (int i = 0; i < Np; ++i) { vx[i] = vy[i] = vz[i] = 0.f; mass[i] = 1.f; phi[i] = 0.f; id[i] = i; mask[i] = 0; }
     float zero[3] = {0.f, 0.f, 0.f}, top[3] = {L, L, L};
 
-    RCBMonopoleForceTree *sft = new RCBMonopoleForceTree(zero, top, zero, top, Np, x, y, z, vx, vy, vz, mass, phi, id, mask,
-                                                         1.0, fg.rmax(), rsm, theta, ppn, 2, 128, fl, 1.0f);
-    delete sft;
+    if (quad) {
+      RCBQuadrupoleForceTree *sft = new RCBQuadrupoleForceTree(zero, top, zero, top, Np, x, y, z, vx, vy, vz, mass, phi, id,
+                                                               mask, 1.0, fg.rmax(), rsm, theta, ppn, 2, 128, fl, 1.0f);
+      delete sft;
+    } else {
+      RCBMonopoleForceTree *sft = new RCBMonopoleForceTree(zero, top, zero, top, Np, x, y, z, vx, vy, vz, mass, phi, id, mask,
+                                                           1.0, fg.rmax(), rsm, theta, ppn, 2, 128, fl, 1.0f);
+      delete sft;
+    }
 
     // the tree reordered the arrays: find the test particle by id (ForceTreeTest.cxx:268-272 searches by x)
     int pidx = 0;
@@ -80,7 +88,7 @@ int main(int argc, char **argv) {
     if (rel > worst) worst = rel;
     if (!(rel <= tol)) { ++bad; printf("trial %d: tree (%g %g %g) direct (%g %g %g) rel %g\n", t, vx[pidx], vy[pidx], vz[pidx], d[0], d[1], d[2], rel); }
   }
-  printf("facade_test law=%s theta=%g ppn=%d nSphere=%d trials=%d: worst relative error %.3e (tolerance %.1e) -> %s\n", law,
+  printf("facade_test %s law=%s theta=%g ppn=%d nSphere=%d trials=%d: worst relative error %.3e (tolerance %.1e) -> %s\n", quad ? "quadrupole" : "monopole", law,
          theta, ppn, nSphere, trials, worst, tol, bad ? "FAIL" : "ok");
   haccsr_facade_release();
   delete fl; delete ev;

@@ -579,3 +579,18 @@ def test_full_size_properties():
         assert abs(v.sum()) < 1e-6 * np.abs(v).sum()
     assert 7000 < st["pairs_evaluated"] / n < 12000
     del torch
+
+
+@pytest.mark.parametrize("law,theta,quad", [("poly", 0.5, False), ("fit", 0.1, False), ("interp", 0.5, False), ("newton", 0.5, False),
+                                            ("poly", 0.5, True), ("fit", 0.5, True)])
+def test_cxx_facade_force_tree_test(law, theta, quad):
+    """tests/cxx/facade_test: the reference's ForceTreeTest scenario (src/halo_finder/ForceTreeTest.cxx:188-302) compiled
+    against the facade headers -- RCBMonopoleForceTree / RCBQuadrupoleForceTree constructed exactly like the reference's
+    call site, tree kick of a test particle against the direct sum with the same ForceLaw object."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(__file__), "cxx", "facade_test")
+    assert os.path.exists(exe), "build it with __graft_entry__.build()"
+    cmd = [exe, law, str(theta), "64", "6000", "4", "2e-5"] + (["quad"] if quad else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, HACCSR_QUIET="1"), timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "-> ok" in r.stdout
