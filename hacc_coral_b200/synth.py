@@ -144,7 +144,7 @@ def zeldovich(ns, z=50.0, seed=5009888, ghost=11, growth_boost=1.0, dtype=np.flo
     return _pack(pos[:, 0], pos[:, 1], pos[:, 2])
 
 
-def zeldovich_torch(ns, z=50.0, seed=5009888, ghost=11, growth_boost=1.0, device="cuda"):
+def zeldovich_torch(ns, z=50.0, seed=5009888, ghost=11, growth_boost=1.0, device="cuda", return_tensor=False):
     """Same recipe as zeldovich() evaluated with torch FFTs on `device` (used by bench.py so that a
     256^3 snapshot takes seconds).  Returns the usual dict of numpy arrays (host)."""
     import torch
@@ -188,6 +188,8 @@ def zeldovich_torch(ns, z=50.0, seed=5009888, ghost=11, growth_boost=1.0, device
         shape[ax] = ns
         pos.append(torch.remainder(g.reshape(shape) + D * psi / c["spacing"], ns).reshape(-1))
     pos = torch.stack(pos, dim=1)
+    if return_tensor:          # (ns^3, 3) float64 positions in [0, ns) on `device`, no ghost shell
+        return pos
     if ghost > 0:
         out = []
         for sx in (-1, 0, 1):
