@@ -6,7 +6,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 HOST = os.path.join(_HERE, "host")
-SOURCES = ["api.cu", "tree_build.cu", "walk.cu", "force.cu", "refresh.cu"]
+SOURCES = ["api.cu", "tree_build.cu", "walk.cu", "force.cu", "refresh.cu", "cic.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

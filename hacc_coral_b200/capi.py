@@ -77,6 +77,8 @@ def load_library():
     lib.haccsr_subcycle.argtypes = [vp, C.c_int, C.c_float, fp, fp, fp, fp, fp, C.c_float, C.c_int64, C.c_int, C.c_float,
                                     C.POINTER(KickStats)]
     i32p = C.POINTER(C.c_int32)
+    lib.haccsr_cic.argtypes = [vp, i32p, C.c_float, vp, C.c_int]
+    lib.haccsr_inverse_cic.argtypes = [vp, i32p, vp, C.c_int, C.c_float, C.c_float, C.c_int]
     lib.haccsr_refresh_message_bytes.restype = C.c_int64
     lib.haccsr_refresh_message_bytes.argtypes = [C.c_int64]
     lib.haccsr_refresh_begin.argtypes = [vp, fp, fp, C.c_float, i32p, ip64, ip64]
@@ -95,7 +97,7 @@ def load_library():
 EXPORTS = ["haccsr_last_error", "haccsr_device_count", "haccsr_create", "haccsr_destroy", "haccsr_set_stream",
            "haccsr_set_force_law", "haccsr_set_arithmetic", "haccsr_upload", "haccsr_download", "haccsr_host_register",
            "haccsr_host_unregister", "haccsr_kick", "haccsr_kick_host", "haccsr_stream", "haccsr_partition_in_box",
-           "haccsr_fill_mass", "haccsr_subcycle", "haccsr_refresh_message_bytes", "haccsr_refresh_begin",
+           "haccsr_fill_mass", "haccsr_subcycle", "haccsr_cic", "haccsr_inverse_cic", "haccsr_refresh_message_bytes", "haccsr_refresh_begin",
            "haccsr_refresh_pack", "haccsr_refresh_append", "haccsr_resident", "haccsr_get_tree", "haccsr_get_pseudo_particles",
            "haccsr_get_lists"]
 
@@ -219,6 +221,20 @@ class HaccSR:
         self._check(self.lib.haccsr_subcycle(self._h, int(nsub), prefactor_tau, _f3(box_hi), _f3(tree_lo), _f3(tree_hi),
                                              _f3(force_lo), _f3(force_hi), theta, int(ppn), tdpts, fcoeff, C.byref(st)))
         return st.as_dict()
+
+    # ---- PM coupling (csrc/cic.cu) ----
+    def cic(self, ng, c):
+        """Particles::cic on the resident particles; returns the (ng0, ng1, ng2) float32 density grid."""
+        ng3 = (C.c_int32 * 3)(*[int(t) for t in ng])
+        rho = np.empty(tuple(int(t) for t in ng), dtype=np.float32)
+        self._check(self.lib.haccsr_cic(self._h, ng3, float(c), C.c_void_p(rho.ctypes.data), 0))
+        return rho
+
+    def inverse_cic(self, grid, tau, fscal, comp):
+        """Particles::inverse_cic: v[comp] += interp(grid) * fscal * tau on the resident particles."""
+        grid = np.ascontiguousarray(grid, dtype=np.float32)
+        ng3 = (C.c_int32 * 3)(*grid.shape)
+        self._check(self.lib.haccsr_inverse_cic(self._h, ng3, C.c_void_p(grid.ctypes.data), 0, float(tau), float(fscal), int(comp)))
 
     # ---- overload refresh (device part; hacc_coral_b200/refresh.py drives it) ----
     def refresh_message_bytes(self, n):

@@ -146,6 +146,10 @@ struct haccsr_ctx {
   haccsr::DevBuf<unsigned> lpt_hist;
   int64_t n_items = 0;
 
+  // PM coupling (cic.cu): fixed-point deposit accumulators and a staging copy of the grid
+  haccsr::DevBuf<unsigned long long> cic_acc;
+  haccsr::DevBuf<float> cic_grid;
+
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // haccsr_kick_host: second stream + events so that the copies of the arrays the tree build does not read
   // (H2D) and of the arrays the force kernel does not write (D2H) hide behind the kernels

@@ -176,6 +176,24 @@ int haccsr_subcycle(haccsr_ctx *ctx, int nsub, float prefactor_tau, const float 
                     const float tree_hi[3], const float force_lo[3], const float force_hi[3], float theta,
                     int64_t ppn, int tdpts, float fcoeff, haccsr_stats *stats);
 
+/* ---- PM coupling: the particle side of the long-range step -------------------------------------
+ * The FFT Poisson solver stays the reference's; these two calls replace the particle loops either side of it so the
+ * particles need not leave the GPU between sub-cycles.  Grids are ng[0]*ng[1]*ng[2] floats, index (ix*ng[1]+iy)*ng[2]+iz
+ * (Particles::array_index, src/cpu/Particles.cxx:373-395), GRID_T = float (-DGRID_32); grid_on_device != 0 means the
+ * pointer is a device pointer.
+ *
+ * haccsr_cic: cloud-in-cell deposit of all resident particles, rho (overwritten) = sum over particles of c * wx wy wz on
+ * the 8 cells around each; cells outside the grid are dropped (the reference's `safe` slot).
+ * Replaces: Particles::cic (src/cpu/Particles.cxx:589-643; c = m_gpscal^3).  Order-independent (fixed-point atomics), equal
+ * to the reference's sequential float sums to FP32 rounding. */
+int haccsr_cic(haccsr_ctx *ctx, const int32_t ng[3], float c, float *rho, int grid_on_device);
+/* haccsr_inverse_cic: v[comp] += (CIC interpolation of grid at the particle) * fscal * tau for all resident particles;
+ * comp 0, 1, 2 = vx, vy, vz, 3 = phi.  Replaces: Particles::inverse_cic(tau, fscal, comp) (src/cpu/Particles.cxx:647-714),
+ * called once per gradient component by map2_poisson_backward_gradient (src/simulation/mc3.cxx:336-379).  Bit-identical
+ * to the reference's loop (same weights, same promotions, same order of the 8 terms). */
+int haccsr_inverse_cic(haccsr_ctx *ctx, const int32_t ng[3], const float *grid, int grid_on_device, float tau, float fscal,
+                       int comp);
+
 /* ---- overload (ghost-zone) refresh: the per-rank, on-device part ---------------------------------------------------
  * Replaces ParticleExchange::exchangeParticles as driven by MC3Extras::refreshParticles at refresh steps
  * (src/simulation/MC3Extras.cxx:660-706; src/halo_finder/ParticleExchange.cxx:488-762), in the local grid units

@@ -657,3 +657,53 @@ void orc_direct_sum(int64_t n, const float *x, const float *y, const float *z, c
     ax[s] = sx; ay[s] = sy; az[s] = sz;
   }
 }
+
+/* ---- PM coupling: Particles::cic / Particles::inverse_cic (src/cpu/Particles.cxx:589-643, 647-714) ---------------------
+ * PARITY UNPINNED against the running reference: Particles.cxx needs MPI, Domain and the initializer headers and cannot
+ * be compiled here.  Restated line by line under C's promotion rules (`1.0` literals are double);
+ * pinned by properties in tests/test_cic_cpu.py (mass conservation, exact interpolation of linear fields, adjointness). */
+static int64_t orc_array_index(int xx, int yy, int zz, const int *ng, int64_t safe) {          /* :373-395 */
+  if (xx >= 0 && xx < ng[0] && yy >= 0 && yy < ng[1] && zz >= 0 && zz < ng[2]) return ((int64_t)xx * ng[1] + yy) * ng[2] + zz;
+  return safe;
+}
+/* rho: ng0*ng1*ng2 + 1 floats (the last one is the `safe` overflow slot) */
+void orc_cic(int64_t np, const float *x, const float *y, const float *z, const int *ng, float c, float *rhoArr) {
+  const int64_t Ng = (int64_t)ng[0] * ng[1] * ng[2], safe = Ng;
+  memset(rhoArr, 0, sizeof(float) * (size_t)(Ng + 1));
+  for (int64_t nn = 0; nn < np; nn++) {
+    float xx = x[nn], yy = y[nn], zz = z[nn];
+    int ix = (int)floorf(xx), iy = (int)floorf(yy), iz = (int)floorf(zz);
+    int ip = ix + 1, jp = iy + 1, kp = iz + 1;
+    float ab = 1.0 + (ix - xx), de = 1.0 + (iy - yy), gh = 1.0 + (iz - zz);
+    rhoArr[orc_array_index(ix, iy, iz, ng, safe)] += c*ab*de*gh;
+    rhoArr[orc_array_index(ix, jp, iz, ng, safe)] += c*ab*(1.0-de)*gh;
+    rhoArr[orc_array_index(ix, jp, kp, ng, safe)] += c*ab*(1.0-de)*(1.0-gh);
+    rhoArr[orc_array_index(ix, iy, kp, ng, safe)] += c*ab*de*(1.0-gh);
+    rhoArr[orc_array_index(ip, iy, kp, ng, safe)] += c*(1.0-ab)*de*(1.0-gh);
+    rhoArr[orc_array_index(ip, jp, kp, ng, safe)] += c*(1.0-ab)*(1.0-de)*(1.0-gh);
+    rhoArr[orc_array_index(ip, jp, iz, ng, safe)] += c*(1.0-ab)*(1.0-de)*gh;
+    rhoArr[orc_array_index(ip, iy, iz, ng, safe)] += c*(1.0-ab)*de*gh;
+  }
+}
+/* grad_phi: ng0*ng1*ng2 + 1 floats; the overflow slot is set to 0 (:677) */
+void orc_inverse_cic(int64_t np, const float *x, const float *y, const float *z, float *vel, const int *ng,
+                     float *grad_phi, float tau, float fscal) {
+  const int64_t Ng = (int64_t)ng[0] * ng[1] * ng[2], safe = Ng;
+  grad_phi[safe] = 0.0;
+  for (int64_t nn = 0; nn < np; nn++) {
+    float xx = x[nn], yy = y[nn], zz = z[nn];
+    int ix = (int)floorf(xx), iy = (int)floorf(yy), iz = (int)floorf(zz);
+    int ip = ix + 1, jp = iy + 1, kp = iz + 1;
+    float ab = 1.0 + (ix - xx), de = 1.0 + (iy - yy), gh = 1.0 + (iz - zz);
+    float f = 0;
+    f += grad_phi[orc_array_index(ix, iy, iz, ng, safe)]*ab*de*gh;
+    f += grad_phi[orc_array_index(ix, jp, iz, ng, safe)]*ab*(1.0-de)*gh;
+    f += grad_phi[orc_array_index(ix, jp, kp, ng, safe)]*ab*(1.0-de)*(1.0-gh);
+    f += grad_phi[orc_array_index(ix, iy, kp, ng, safe)]*ab*de*(1.0-gh);
+    f += grad_phi[orc_array_index(ip, iy, kp, ng, safe)]*(1.0-ab)*de*(1.0-gh);
+    f += grad_phi[orc_array_index(ip, jp, kp, ng, safe)]*(1.0-ab)*(1.0-de)*(1.0-gh);
+    f += grad_phi[orc_array_index(ip, jp, iz, ng, safe)]*(1.0-ab)*(1.0-de)*gh;
+    f += grad_phi[orc_array_index(ip, iy, iz, ng, safe)]*(1.0-ab)*de*gh;
+    vel[nn] += f*fscal*tau;
+  }
+}

@@ -51,6 +51,9 @@ def _lib():
         lib.orc_get_lists.argtypes = [C.c_void_p, ip, ip, ip, C.POINTER(C.c_uint8)]
         lib.orc_free.argtypes = [C.c_void_p]
         lib.orc_set_tdpts.argtypes = [C.c_int]
+        i32p = C.POINTER(C.c_int32)
+        lib.orc_cic.argtypes = [C.c_int64, fp, fp, fp, i32p, C.c_float, fp]
+        lib.orc_inverse_cic.argtypes = [C.c_int64, fp, fp, fp, fp, i32p, fp, C.c_float, C.c_float]
         lib.orc_get_pp12.argtypes = [C.c_void_p, fp]
         dp = C.POINTER(C.c_double)
         lib.orc_direct_sum.argtypes = [C.c_int64, fp, fp, fp, fp, C.c_int64, ip, fp, C.c_int, C.c_float,
@@ -136,3 +139,24 @@ def force_law_eval(r2, rsm, rmax=RMAX, coef=POLY5, law=LAW_POLY):
     coef = np.ascontiguousarray(coef, dtype=np.float32)
     _lib().orc_force_law_eval(law, _fp(coef), len(coef), rsm, float(rmax), r2.size, _fp(r2), _fp(out))
     return out
+
+
+def cic(p, ng, c):
+    """Particles::cic restated (src/cpu/Particles.cxx:589-643): returns the (ng0, ng1, ng2) float32 grid."""
+    x, y, z = (np.ascontiguousarray(p[k], dtype=np.float32) for k in ("x", "y", "z"))
+    ng3 = np.asarray(ng, dtype=np.int32)
+    rho = np.empty(int(np.prod(ng3.astype(np.int64))) + 1, dtype=np.float32)
+    _lib().orc_cic(x.size, _fp(x), _fp(y), _fp(z), ng3.ctypes.data_as(C.POINTER(C.c_int32)), float(c), _fp(rho))
+    return rho[:-1].reshape(tuple(int(t) for t in ng3))
+
+
+def inverse_cic(p, grid, tau, fscal, comp):
+    """Particles::inverse_cic restated (:647-714): returns the kicked copy of v[comp] (comp 3 = phi)."""
+    x, y, z = (np.ascontiguousarray(p[k], dtype=np.float32) for k in ("x", "y", "z"))
+    v = np.ascontiguousarray(p[("vx", "vy", "vz", "phi")[comp]], dtype=np.float32).copy()
+    grid = np.ascontiguousarray(grid, dtype=np.float32)
+    ng3 = np.asarray(grid.shape, dtype=np.int32)
+    g = np.concatenate([grid.ravel(), np.zeros(1, np.float32)])
+    _lib().orc_inverse_cic(x.size, _fp(x), _fp(y), _fp(z), _fp(v), ng3.ctypes.data_as(C.POINTER(C.c_int32)), _fp(g),
+                           float(tau), float(fscal))
+    return v
