@@ -41,6 +41,8 @@ def parse():
                     help="cut-out side (cells) for the CPU baseline: 112^3 cells = 1.4 M particles = about 10 s on 16 cores")
     ap.add_argument("--arith", default="fused", choices=["fused", "x86"], help="pair-kernel arithmetic (include/haccsr.h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cull", action="store_true", help="headline run with warp-level culling on (haccsr_set_culling); "
+                    "by default culling is off and only a side measurement of it is reported under 'culled'")
     return ap.parse_args()
 
 
@@ -188,6 +190,7 @@ def main():
         pin[k] = t.numpy()
     g = H.HaccSR(n, device=local, arith=H.ARITH_FUSED if args.arith == "fused" else H.ARITH_X86)
     g.set_force_law(H.LAW_SR_POLY, H.POLY5, RSM, H.RMAX)
+    g.set_culling(args.cull)
     stream = torch.cuda.current_stream()
     g.set_stream(stream.cuda_stream)
     lo, hi = [0.0] * 3, [float(nglt)] * 3
@@ -240,6 +243,19 @@ def main():
     g.upload(pin)
     # one untimed pass that also counts the pairs inside the cutoff (honest-metric companion number)
     stc = g.kick(lo, hi, flo, fhi, THETA, args.ppn, count_in_cutoff=True)
+    # side measurement: the same kick with warp-level culling (bit-identical result, fewer executed flops)
+    culled = None
+    if args.arith == "fused":
+        g.set_culling(not args.cull)
+        g.kick(lo, hi, flo, fhi, THETA, args.ppn)
+        other = [g.kick(lo, hi, flo, fhi, THETA, args.ppn) for _ in range(3)]
+        oc = g.kick(lo, hi, flo, fhi, THETA, args.ppn, count_in_cutoff=True)
+        g.set_culling(args.cull)
+        on, off_ms = (stc, np.mean([o["ms_force"] for o in other])) if args.cull else (oc, ms_force / args.steps)
+        on_ms = ms_force / args.steps if args.cull else np.mean([o["ms_force"] for o in other])
+        culled = {"ms_force": float(on_ms), "ms_force_unculled": float(off_ms), "speedup_force": float(off_ms / on_ms),
+                  "pairs_force_law_frac": on["pairs_force_law"] / max(on["pairs_evaluated"], 1),
+                  "note": "warp-level early exit after the cutoff test; results bit-identical; off in the headline unless --cull"}
 
     tv = torch.tensor([ms, ms_e2e, ms_force], device=dev, dtype=torch.float64)
     sv = torch.tensor([float(pairs), float(pairs_e2e), float(launches)], device=dev, dtype=torch.float64)
@@ -283,6 +299,15 @@ def main():
                  "max_list": st["max_list"], "pseudo_particles": st["pseudo_particles"]},
         "clocks": sampler.summary(),
     }
+    if culled:
+        line["culled"] = culled
+    if args.cull:
+        # with culling the kernel executes 30 flop only for the pairs that reach the force law and 9 (three differences,
+        # the r2 chain, the softening add) for the rest: report the executed rate next to the algorithmic one
+        ex = (30.0 * stc["pairs_force_law"] + 9.0 * (stc["pairs_evaluated"] - stc["pairs_force_law"])) / max(stc["pairs_evaluated"], 1)
+        line["roofline"]["executed_flop_per_interaction"] = ex
+        line["roofline"]["frac_executed"] = line["roofline"]["frac"] * ex / FLOP_PER_PAIR
+        line["config"]["culling"] = "on"
     if not args.no_cpu_baseline:
         try:
             info = run_reference_sample(p, nglt, args)

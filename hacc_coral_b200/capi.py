@@ -27,7 +27,7 @@ class KickStats(C.Structure):
                 ("pseudo_particles", C.c_int64), ("max_list", C.c_int64), ("pairs_evaluated", C.c_uint64),
                 ("pairs_in_cutoff", C.c_uint64), ("ms_build", C.c_float), ("ms_walk", C.c_float),
                 ("ms_force", C.c_float), ("ms_total", C.c_float), ("force_launches", C.c_int32),
-                ("total_launches", C.c_int32)]
+                ("total_launches", C.c_int32), ("pairs_force_law", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -63,6 +63,7 @@ def load_library():
     lib.haccsr_set_stream.argtypes = [vp, vp]
     lib.haccsr_set_force_law.argtypes = [vp, C.c_int, fp, C.c_int, C.c_float, C.c_float]
     lib.haccsr_set_arithmetic.argtypes = [vp, C.c_int]
+    lib.haccsr_set_culling.argtypes = [vp, C.c_int]
     lib.haccsr_upload.argtypes = [vp, C.c_int64] + [fp] * 8 + [ip64, u16p]
     lib.haccsr_download.argtypes = [vp, C.c_int64] + [fp] * 8 + [ip64, u16p]
     lib.haccsr_host_register.argtypes = [vp, C.c_size_t]
@@ -95,7 +96,7 @@ def load_library():
 
 
 EXPORTS = ["haccsr_last_error", "haccsr_device_count", "haccsr_create", "haccsr_destroy", "haccsr_set_stream",
-           "haccsr_set_force_law", "haccsr_set_arithmetic", "haccsr_upload", "haccsr_download", "haccsr_host_register",
+           "haccsr_set_force_law", "haccsr_set_arithmetic", "haccsr_set_culling", "haccsr_upload", "haccsr_download", "haccsr_host_register",
            "haccsr_host_unregister", "haccsr_kick", "haccsr_kick_host", "haccsr_stream", "haccsr_partition_in_box",
            "haccsr_fill_mass", "haccsr_subcycle", "haccsr_cic", "haccsr_inverse_cic", "haccsr_refresh_message_bytes", "haccsr_refresh_begin",
            "haccsr_refresh_pack", "haccsr_refresh_append", "haccsr_resident", "haccsr_get_tree", "haccsr_get_pseudo_particles",
@@ -144,6 +145,9 @@ class HaccSR:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.haccsr_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_culling(self, on):
+        self._check(self.lib.haccsr_set_culling(self._h, int(bool(on))))
 
     def set_arithmetic(self, mode):
         self._check(self.lib.haccsr_set_arithmetic(self._h, int(mode)))

@@ -254,6 +254,12 @@ int haccsr_set_force_law(haccsr_ctx *c, int kind, const float *coeffs, int ncoef
   return 0;
 }
 
+int haccsr_set_culling(haccsr_ctx *c, int on) {
+  if (!c) { set_error("null context"); return 1; }
+  c->cull = on ? 1 : 0;
+  return 0;
+}
+
 int haccsr_set_arithmetic(haccsr_ctx *c, int mode) {
   if (!c) { set_error("null context"); return 1; }
   if (mode != HACCSR_ARITH_FUSED && mode != HACCSR_ARITH_X86) { set_error("unknown arithmetic mode %d", mode); return 1; }

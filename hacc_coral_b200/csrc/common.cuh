@@ -109,6 +109,7 @@ struct haccsr_ctx {
   haccsr::ForceLawParams law{};
   bool law_set = false;
   int arith = HACCSR_ARITH_FUSED;
+  int cull = 0;                                     // warp-level culling in the pair kernel (haccsr_set_culling)
   haccsr::DevBuf<float> law_table;                  // SR_INTERP: f[ntab] then r2[ntab]
 
   // build scratch

@@ -136,6 +136,50 @@ __device__ __forceinline__ void interact1_fused(const float4 s, SinkRegs1 &k, co
   if (COUNT) cnt += (in && t > P.rsm2) ? 1u : 0u;
 }
 
+// CULL (haccsr_set_culling, fused arithmetic only): the same sequence with a warp-level early exit.  Of the pairs the
+// reference's lists make the kernel look at, 98 % lie outside the cutoff and contribute nothing; with
+// sinks spread over lanes, the 64 sinks a packed instruction serves are neighbours in tree order, and for ~86 % of the
+// sources none of them is inside the cutoff.  One vote after the cutoff test then skips the polynomial, the rsqrt and
+// the accumulate for the whole warp.  Results are bit-identical to the unculled kernel: a skipped pair is exactly a
+// pair whose accumulate predicate was false.  `nfull` counts the lane-pairs that ran the force law (COUNT variant).
+template <int NC, bool GUARD0, bool COUNT, bool UNITM>
+__device__ __forceinline__ void interact2_cull(const float4 s, SinkRegs2 &k, const ForceParams &P, unsigned &cnt_a, unsigned &cnt_b,
+                                               unsigned &nf_a, unsigned &nf_b) {
+  const float2 dx = __fadd2_rn(make_float2(s.x, s.x), k.nx), dy = __fadd2_rn(make_float2(s.y, s.y), k.ny),
+               dz = __fadd2_rn(make_float2(s.z, s.z), k.nz);
+  float2 t = __ffma2_rn(dx, dx, make_float2(P.rsm2, P.rsm2));
+  t = __ffma2_rn(dy, dy, t);
+  t = __ffma2_rn(dz, dz, t);
+  bool in_a = t.x < P.smax, in_b = t.y < P.smax;
+  if (GUARD0) { in_a = in_a && (t.x > P.rsm2); in_b = in_b && (t.y > P.rsm2); }
+  if (!__any_sync(0xffffffffu, in_a || in_b)) return;
+  float2 p = make_float2(P.b[NC - 1], P.b[NC - 1]);
+#pragma unroll
+  for (int q = NC - 2; q >= 0; --q) p = __ffma2_rn(p, t, make_float2(P.b[q], P.b[q]));
+  const float2 rs = make_float2(rsqrt_ftz(t.x), rsqrt_ftz(t.y));
+  float2 f = __ffma2_rn(__fmul2_rn(rs, rs), rs, p);
+  if (!UNITM) f = __fmul2_rn(f, make_float2(s.w, s.w));
+  if (in_a) { k.ax.x = __fmaf_rn(f.x, dx.x, k.ax.x); k.ay.x = __fmaf_rn(f.x, dy.x, k.ay.x); k.az.x = __fmaf_rn(f.x, dz.x, k.az.x); }
+  if (in_b) { k.ax.y = __fmaf_rn(f.y, dx.y, k.ax.y); k.ay.y = __fmaf_rn(f.y, dy.y, k.ay.y); k.az.y = __fmaf_rn(f.y, dz.y, k.az.y); }
+  if (COUNT) { cnt_a += (in_a && t.x > P.rsm2) ? 1u : 0u; cnt_b += (in_b && t.y > P.rsm2) ? 1u : 0u; nf_a++; nf_b++; }
+}
+template <int NC, bool GUARD0, bool COUNT, bool UNITM>
+__device__ __forceinline__ void interact1_cull(const float4 s, SinkRegs1 &k, const ForceParams &P, unsigned &cnt, unsigned &nfull) {
+  const float dx = __fadd_rn(s.x, k.nx), dy = __fadd_rn(s.y, k.ny), dz = __fadd_rn(s.z, k.nz);
+  const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, P.rsm2)));
+  bool in = t < P.smax;
+  if (GUARD0) in = in && (t > P.rsm2);
+  if (!__any_sync(0xffffffffu, in)) return;
+  float p = P.b[NC - 1];
+#pragma unroll
+  for (int q = NC - 2; q >= 0; --q) p = __fmaf_rn(p, t, P.b[q]);
+  const float rs = rsqrt_ftz(t);
+  float f = __fmaf_rn(__fmul_rn(rs, rs), rs, p);
+  if (!UNITM) f = __fmul_rn(f, s.w);
+  if (in) { k.ax = __fmaf_rn(f, dx, k.ax); k.ay = __fmaf_rn(f, dy, k.ay); k.az = __fmaf_rn(f, dz, k.az); }
+  if (COUNT) { cnt += (in && t > P.rsm2) ? 1u : 0u; nfull += 1u; }
+}
+
 template <int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM>
 __device__ __forceinline__ void interact2(const float4 s, SinkRegs2 &k, const ForceParams &P, unsigned &cnt_a, unsigned &cnt_b) {
   const float2 dx = __fadd2_rn(make_float2(s.x, s.x), k.nx), dy = __fadd2_rn(make_float2(s.y, s.y), k.ny),
@@ -242,7 +286,7 @@ __device__ __noinline__ void produce_tile(Producer &pr, const ForceParams &P, fl
 // ~130 instructions): the eight (S2, ODD) variants together fit the 32 KB instruction cache, which the first
 // version's 4x-unrolled bodies (72 KB) did not -- that showed as "no_instruction" stalls, worst on clustered
 // snapshots where all eight variants are in flight on one SM.
-template <int S2, int S1, int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM, bool FUSED>
+template <int S2, int S1, int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM, int FUSED>
 __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P, float4 (*tiles)[FTILE],
                                          unsigned long long *bars) {
   constexpr int S = 2 * S2 + S1;      // S1 scalar groups follow the S2 packed pairs
@@ -279,8 +323,9 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
     for (int s = 0; s < FSTAGES; ++s) produce_tile(pr, P, tiles[s], smem_u32(&bars[s]));
   }
   unsigned cnt[S];
+  unsigned nf[S];           // FUSED == 2, COUNT: pairs of this thread's sinks that ran the force law
 #pragma unroll
-  for (int g = 0; g < S; ++g) cnt[g] = 0;
+  for (int g = 0; g < S; ++g) { cnt[g] = 0; nf[g] = 0; }
   for (unsigned t = 0; t < ntiles; ++t) {
     const int stage = t % FSTAGES;
     const unsigned parity = (t / FSTAGES) & 1u;
@@ -292,12 +337,14 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
       const float4 s = tile[j];
 #pragma unroll
       for (int k = 0; k < S2; ++k) {
-        if (FUSED) interact2_fused<NC, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
+        if (FUSED == 2) interact2_cull<NC, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1], nf[2 * k], nf[2 * k + 1]);
+        else if (FUSED) interact2_fused<NC, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
         else interact2<NC, LAW, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
       }
 #pragma unroll
       for (int k = 0; k < S1; ++k) {
-        if (FUSED) interact1_fused<NC, GUARD0, COUNT, UNITM>(s, k1[k], P, cnt[2 * S2 + k]);
+        if (FUSED == 2) interact1_cull<NC, GUARD0, COUNT, UNITM>(s, k1[k], P, cnt[2 * S2 + k], nf[2 * S2 + k]);
+        else if (FUSED) interact1_fused<NC, GUARD0, COUNT, UNITM>(s, k1[k], P, cnt[2 * S2 + k]);
         else interact1<NC, LAW, GUARD0, COUNT, UNITM>(s, k1[k], P, cnt[2 * S2 + k]);
       }
     }
@@ -325,10 +372,17 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
     for (int g = 0; g < S; ++g) c64 += (g * 32 + lane < it.sink_count) ? cnt[g] : 0u;
     for (int o = 16; o > 0; o >>= 1) c64 += __shfl_down_sync(0xffffffffu, c64, o);
     if (lane == 0) atomicAdd(P.incut, c64);
+    if (FUSED == 2) {
+      unsigned long long f64 = 0;
+#pragma unroll
+      for (int g = 0; g < S; ++g) f64 += (g * 32 + lane < it.sink_count) ? nf[g] : 0u;
+      for (int o = 16; o > 0; o >>= 1) f64 += __shfl_down_sync(0xffffffffu, f64, o);
+      if (lane == 0) atomicAdd(P.incut + 1, f64);
+    }
   }
 }
 
-template <int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM, bool FUSED>
+template <int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM, int FUSED>
 __device__ __forceinline__ void dispatch_item(int S, const WorkItem it, const ForceParams &P, float4 (*tiles)[FTILE],
                                               unsigned long long *bars) {
   switch (S) {
@@ -343,7 +397,7 @@ __device__ __forceinline__ void dispatch_item(int S, const WorkItem it, const Fo
   }
 }
 
-template <int NC, int LAW, bool GUARD0, bool COUNT, bool FUSED>
+template <int NC, int LAW, bool GUARD0, bool COUNT, int FUSED>
 __global__ void __launch_bounds__(32) k_force(const __grid_constant__ ForceParams P, int n_items) {
   __shared__ __align__(128) float4 tiles[FSTAGES][FTILE];
   __shared__ __align__(8) unsigned long long bars[FSTAGES];
@@ -427,7 +481,7 @@ __global__ void k_lpt_scatter(const WorkItem *__restrict__ items, const unsigned
   out[atomicAdd(&cursor[lpt_bin(w, list_len, groups, n_part)], 1u)] = w;
 }
 
-template <int NC, int LAW, bool GUARD0, bool FUSED = false>
+template <int NC, int LAW, bool GUARD0, int FUSED = 0>
 static int launch_force(haccsr_ctx *c, const ForceParams &P0, int n_items, bool count) {
   // one launch per group of items (a single group unless haccsr_kick_host asked for range-wise velocity copies)
   const int groups = c->force_groups;
@@ -461,7 +515,7 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   k_item_count<<<(nn + 255) / 256, 256, 0, s>>>(c->nodes.p, c->n_ranges.p, nn, c->item_cnt.p);
   c->launches++;
   HSR_TRY(scan_exclusive(c, c->item_cnt.p, c->item_off.p, nn, c->d_counters + 10));
-  HSR_CUDA(cudaMemsetAsync(c->d_counters + 11, 0, sizeof(unsigned long long), s));
+  HSR_CUDA(cudaMemsetAsync(c->d_counters + 11, 0, 2 * sizeof(unsigned long long), s));   // in-cutoff pairs, force-law pairs
   HSR_CUDA(cudaMemcpyAsync(c->h_counters + 10, c->d_counters + 10, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   HSR_CUDA(cudaStreamSynchronize(s));
   c->n_items = c->h_counters[10];
@@ -512,17 +566,22 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   else if (c->law.kind == HACCSR_LAW_SR_INTERP) rc = guard0 ? launch_force<1, 3, true>(c, P, ni, count_in_cutoff) : launch_force<1, 3, false>(c, P, ni, count_in_cutoff);
   else {
     const bool guard = !(c->law.rsm2 > 0.0f);
-    if (c->arith == HACCSR_ARITH_FUSED) {
-      if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true, true>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false, true>(c, P, ni, count_in_cutoff);
-      else rc = guard ? launch_force<7, 0, true, true>(c, P, ni, count_in_cutoff) : launch_force<7, 0, false, true>(c, P, ni, count_in_cutoff);
+    if (c->arith == HACCSR_ARITH_FUSED && c->cull) {
+      if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true, 2>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false, 2>(c, P, ni, count_in_cutoff);
+      else rc = guard ? launch_force<7, 0, true, 2>(c, P, ni, count_in_cutoff) : launch_force<7, 0, false, 2>(c, P, ni, count_in_cutoff);
+    } else if (c->arith == HACCSR_ARITH_FUSED) {
+      if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true, 1>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false, 1>(c, P, ni, count_in_cutoff);
+      else rc = guard ? launch_force<7, 0, true, 1>(c, P, ni, count_in_cutoff) : launch_force<7, 0, false, 1>(c, P, ni, count_in_cutoff);
     } else if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false>(c, P, ni, count_in_cutoff);
     else rc = guard ? launch_force<7, 0, true>(c, P, ni, count_in_cutoff) : launch_force<7, 0, false>(c, P, ni, count_in_cutoff);
   }
   if (rc) return rc;
   if (count_in_cutoff && st) {
-    HSR_CUDA(cudaMemcpyAsync(c->h_counters + 11, c->d_counters + 11, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    HSR_CUDA(cudaMemcpyAsync(c->h_counters + 11, c->d_counters + 11, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     HSR_CUDA(cudaStreamSynchronize(s));
     st->pairs_in_cutoff = (uint64_t)c->h_counters[11];
+    st->pairs_force_law = (c->arith == HACCSR_ARITH_FUSED && c->cull && c->law.kind == HACCSR_LAW_SR_POLY)
+                              ? (uint64_t)c->h_counters[12] : st->pairs_evaluated;
   }
   return 0;
 }

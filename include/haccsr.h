@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HACCSR_VERSION 1
+#define HACCSR_VERSION 2
 
 typedef struct haccsr_ctx haccsr_ctx;
 
@@ -82,6 +82,8 @@ typedef struct haccsr_stats {
   float ms_total;           /* device time of the whole haccsr_kick call                 */
   int32_t force_launches;   /* kernel launches of the force kernel in this call          */
   int32_t total_launches;   /* all kernel launches in this call                          */
+  uint64_t pairs_force_law; /* pairs for which the force law was executed; only when count_in_cutoff != 0.  Equal to
+                               pairs_evaluated unless warp-level culling is on (haccsr_set_culling)            */
 } haccsr_stats;
 
 /* Per-call options of the kick; zero-initialise for defaults. */
@@ -112,6 +114,13 @@ int haccsr_set_force_law(haccsr_ctx *ctx, int kind, const float *coeffs, int nco
 
 /* Select the pair-kernel arithmetic (HACCSR_ARITH_*); context-wide, default HACCSR_ARITH_FUSED. */
 int haccsr_set_arithmetic(haccsr_ctx *ctx, int mode);
+
+/* Warp-level culling in the pair kernel (fused arithmetic, polynomial law): after the cutoff test, a warp none of whose
+ * lanes holds a pair inside the cutoff skips the force law for that source.  The reference evaluates every list pair in
+ * full and multiplies 98 % of them by zero (RCBForceTree.cxx:612-613); skipping them changes no bit of
+ * the result.  Off by default: with it on, the kernel no longer executes the fixed 30 flop per list pair that the
+ * benchmark's roofline accounting assumes (haccsr_stats.pairs_force_law reports what was executed). */
+int haccsr_set_culling(haccsr_ctx *ctx, int on);
 
 /* Copy `count` particles from host arrays into the context (H2D).
  * Replaces: handing m_xArr ... m_maskArr to the constructor (src/cpu/Particles.cxx:1317-1327). */

@@ -594,3 +594,27 @@ def test_cxx_facade_force_tree_test(law, theta, quad):
     r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, HACCSR_QUIET="1"), timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "-> ok" in r.stdout
+
+
+@pytest.mark.parametrize("tdpts", [1, 12])
+def test_culling_changes_no_bit(tdpts):
+    """haccsr_set_culling: the warp-level early exit skips only pairs whose accumulate predicate is false in every lane,
+    so kicks, counts and the tree are bit-identical; pairs_force_law reports how many pairs still ran the force law."""
+    p = synth.clustered(60000, 40.0, seed=77)
+    rng = np.random.default_rng(3)
+    p["mass"] = (0.5 + rng.random(p["x"].size)).astype(np.float32) if tdpts == 12 else p["mass"]
+    b = boxes(40)
+    outs, sts = [], []
+    for on in (False, True):
+        g = H.HaccSR(p["x"].size)
+        g.set_force_law(H.LAW_SR_POLY, H.POLY5, RSM, H.RMAX)
+        g.set_culling(on)
+        g.upload(p)
+        sts.append(g.kick(*b, 0.5, 256, count_in_cutoff=True, tdpts=tdpts))
+        outs.append(g.download())
+        g.close()
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    assert sts[0]["pairs_evaluated"] == sts[1]["pairs_evaluated"] and sts[0]["pairs_in_cutoff"] == sts[1]["pairs_in_cutoff"]
+    assert sts[0]["pairs_force_law"] == sts[0]["pairs_evaluated"]
+    assert sts[1]["pairs_in_cutoff"] <= sts[1]["pairs_force_law"] < 0.8 * sts[1]["pairs_evaluated"]
