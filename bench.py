@@ -36,7 +36,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--np-side", type=int, default=256, help="alive particles per dimension per GPU")
     ap.add_argument("--ppn", type=int, default=512, help="leaf size (reference -N 512, run_hacc.sh:2)")
-    ap.add_argument("--state", default="uniform", choices=["uniform", "clustered"])
+    ap.add_argument("--state", default="uniform", choices=["uniform", "clustered", "clumpy"],
+                    help="uniform = z=50 Zel'dovich (configs[1]); clustered = shell-crossed Zel'dovich (configs[2]); clumpy = "
+                         "clustered + 15 %% of the particles in 64 isothermal knots (stress case: lists beyond the reference's VMAX)")
     ap.add_argument("--sample-side", type=int, default=112,
                     help="cut-out side (cells) for the CPU baseline: 112^3 cells = 1.4 M particles = about 10 s on 16 cores")
     ap.add_argument("--arith", default="fused", choices=["fused", "x86"], help="pair-kernel arithmetic (include/haccsr.h)")
@@ -100,12 +102,15 @@ def make_snapshot(args, rank, device):
     from hacc_coral_b200 import synth
     boost = 1.0
     z = 50.0
-    if args.state == "clustered":
+    if args.state in ("clustered", "clumpy"):
         z, boost = 0.0, 0.35      # Zel'dovich pushed to shell crossing: sheets / filaments / knots
     try:
-        return synth.zeldovich_torch(args.np_side, z=z, seed=5009888 + rank, ghost=GHOST, growth_boost=boost, device=device)
+        p = synth.zeldovich_torch(args.np_side, z=z, seed=5009888 + rank, ghost=GHOST, growth_boost=boost, device=device)
     except Exception:
-        return synth.zeldovich(args.np_side, z=z, seed=5009888 + rank, ghost=GHOST, growth_boost=boost)
+        p = synth.zeldovich(args.np_side, z=z, seed=5009888 + rank, ghost=GHOST, growth_boost=boost)
+    if args.state == "clumpy":
+        synth.add_clumps(p, float(args.np_side + 2 * GHOST), seed=99 + rank)
+    return p
 
 
 def run_reference_sample(p, nglt, args):
@@ -134,7 +139,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     nglt = args.np_side + 2 * GHOST
     workload = "np=%d^3 alive per GPU + %d-cell overload shell (%d^3 grid units), %s Zel'dovich snapshot, ppn=%d, theta=%.1f, poly5" % (
-        args.np_side, GHOST, nglt, "z=50 near-uniform" if args.state == "uniform" else "shell-crossed clustered", args.ppn, THETA)
+        args.np_side, GHOST, nglt, {"uniform": "z=50 near-uniform", "clustered": "shell-crossed clustered", "clumpy": "shell-crossed + isothermal knots"}[args.state], args.ppn, THETA)
     config = {"workload": workload, "np_side": args.np_side, "ppn": args.ppn, "theta": THETA, "rsm": RSM,
               "force_law": "poly5", "arithmetic": args.arith, "state": args.state, "l2": "inputs larger than L2 (no flush needed)",
               "parallelism": "1 sub-volume per GPU, no data-path collective"}

@@ -204,6 +204,26 @@ def zeldovich_torch(ns, z=50.0, seed=5009888, ghost=11, growth_boost=1.0, device
     return _pack(pos[:, 0], pos[:, 1], pos[:, 2])
 
 
+def add_clumps(p, side, frac=0.15, n_clumps=64, seed=99, r_lo=0.4, r_hi=2.5):
+    """Move a fraction of the particles of snapshot p (coordinates in [0, side)) into isothermal (rho ~ r^-2) clumps of
+    radius r_lo..r_hi cells at seeded random centres: halo-like knots of a few 10^4 particles with overdensities of
+    10^3-10^5, which produce the deep interaction lists of an evolved snapshot (state C).  In place."""
+    rng = np.random.default_rng(seed)
+    n = p["x"].size
+    pick = rng.choice(n, int(frac * n), replace=False)
+    centres = rng.random((n_clumps, 3)) * (side - 8.0) + 4.0
+    radius = r_lo + (r_hi - r_lo) * rng.random(n_clumps)
+    which = rng.integers(0, n_clumps, pick.size)
+    r = radius[which] * rng.random(pick.size)                    # uniform in r  =>  rho ~ r^-2
+    u = rng.standard_normal((pick.size, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    q = centres[which] + r[:, None] * u
+    top = np.nextafter(np.float32(side), np.float32(0))
+    for k, a in enumerate(("x", "y", "z")):
+        p[a][pick] = np.clip(q[:, k], 0.0, top).astype(np.float32)
+    return p
+
+
 def cutout(p, lo, hi):
     """Particles of snapshot p inside the cube [lo, hi)^3, shifted to start at 0 (a bounded sample of the
     same workload for the CPU baseline)."""
