@@ -43,6 +43,9 @@ def parse():
                     help="cut-out side (cells) for the CPU baseline: 112^3 cells = 1.4 M particles = about 10 s on 16 cores")
     ap.add_argument("--arith", default="fused", choices=["fused", "x86"], help="pair-kernel arithmetic (include/haccsr.h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--subcycle", type=int, default=0, metavar="NSUB",
+                    help="also time Particles::subCycle on the device (haccsr_subcycle: NSUB x [stream, out-of-box compaction, mass=1, "
+                         "kick, stream], one upload and one download) and report it as the side block 'subcycle' (configs[4])")
     ap.add_argument("--cull", action="store_true", help="headline run with warp-level culling on (haccsr_set_culling); "
                     "by default culling is off and only a side measurement of it is reported under 'culled'")
     return ap.parse_args()
@@ -262,6 +265,33 @@ def main():
                   "pairs_force_law_frac": on["pairs_force_law"] / max(on["pairs_evaluated"], 1),
                   "note": "warp-level early exit after the cutoff test; results bit-identical; off in the headline unless --cull"}
 
+    # side measurement: the full short-range sub-cycle loop of one long step, particles resident between the kicks
+    subc = None
+    if args.subcycle > 0:
+        vmax = max(float(np.abs(pin[k]).max()) for k in ("vx", "vy", "vz"))
+        # each half-stream moves the fastest particle 0.02 cells; the parity snapshots carry v = 0, then only the kicks move them
+        pt = 0.02 / vmax if vmax > 0 else 0.01
+        sub_args = (args.subcycle, pt, [float(nglt)] * 3, lo, hi, flo, fhi, THETA, args.ppn, 1e-3)
+        g.upload(pin)
+        g.subcycle(*sub_args)                         # warm
+        barrier()
+        s0, s1, s2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        s0.record(stream)
+        g.upload(pin)
+        s1.record(stream)
+        sst = g.subcycle(*sub_args)
+        s2.record(stream)
+        g.download(out=work)
+        s3 = torch.cuda.Event(enable_timing=True)
+        s3.record(stream)
+        barrier()
+        subc = {"nsub": args.subcycle, "ms_resident": s1.elapsed_time(s2), "ms_with_transfers": s0.elapsed_time(s3),
+                "pairs_evaluated": int(sst["pairs_evaluated"]), "ms_force": sst["ms_force"], "ms_build": sst["ms_build"],
+                "value": sst["pairs_evaluated"] / (s1.elapsed_time(s2) * 1e-3) / 1e9,
+                "e2e_value": sst["pairs_evaluated"] / (s0.elapsed_time(s3) * 1e-3) / 1e9, "unit": "Ginteractions/s",
+                "note": "haccsr_subcycle = Particles::subCycle (Particles.cxx:1176-1201) on the device; rank 0's numbers"}
+        g.upload(pin)
+
     tv = torch.tensor([ms, ms_e2e, ms_force], device=dev, dtype=torch.float64)
     sv = torch.tensor([float(pairs), float(pairs_e2e), float(launches)], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -306,6 +336,8 @@ def main():
     }
     if culled:
         line["culled"] = culled
+    if subc:
+        line["subcycle"] = subc
     if args.cull:
         # with culling the kernel executes 30 flop only for the pairs that reach the force law and 9 (three differences,
         # the r2 chain, the softening add) for the rest: report the executed rate next to the algorithmic one

@@ -174,7 +174,7 @@ int haccsr_destroy(haccsr_ctx *c) {
   c->lbase.release(); c->nleft.release(); c->tilecount.release(); c->tilebase.release(); c->scratch_u32.release();
   c->n_ranges.release(); c->n_pseudo.release(); c->range_off.release(); c->pseudo_off.release(); c->list_len.release();
   c->ranges.release(); c->pool.release(); c->law_table.release(); c->item_cnt.release(); c->item_off.release(); c->items.release(); c->items_sorted.release(); c->lpt_hist.release(); c->refresh_slots.release();
-  c->pp12.release(); c->split_flag.release(); c->split_rank.release(); c->cic_acc.release(); c->cic_grid.release();
+  c->scan_tmp.release(); c->pp12.release(); c->split_flag.release(); c->split_rank.release(); c->cic_acc.release(); c->cic_grid.release();
   if (c->h_level) cudaFreeHost(c->h_level);
   if (c->d_level) cudaFree(c->d_level);
   if (c->h_counters) cudaFreeHost(c->h_counters);

@@ -124,6 +124,7 @@ struct haccsr_ctx {
   haccsr::DevBuf<unsigned> tilecount, tilebase;     // per tile: left count, exclusive scan
   haccsr::DevBuf<unsigned> split_flag, split_rank;  // per node of the current level: splits (0/1), exclusive scan
   haccsr::DevBuf<unsigned> scratch_u32;             // maxima for the fixed-point scales etc.
+  haccsr::DevBuf<unsigned> scan_tmp;                // scan_exclusive on long inputs: per-block sums and their scan
   haccsr::LevelInfo *h_level = nullptr;             // pinned
   haccsr::LevelInfo *d_level = nullptr;
   int64_t *h_counters = nullptr;                    // pinned, misc read-backs

@@ -9,7 +9,7 @@
 //
 // How it is computed is not the reference's recursion.  All nodes of one level are processed together by
 // passes over fixed 1024-particle tiles (HBM-bound streaming kernels):
-//   A  k_cm_tile        per-tile partial box / centroid sums -> per-node accumulators
+//   A  k_cm_tile        per-warp box / centroid sums by node run -> per-block slots -> per-node accumulators
 //   B  k_level_finalize  one block: box, centroid, split decision, BFS child allocation (prefix scan)
 //   C1 k_left_count     per-tile count of "goes left" flags + local prefixes at node boundaries
 //   C2 k_scan           exclusive scan of tile counts  => global prefix L(i) of left flags
@@ -33,7 +33,6 @@ namespace haccsr {
 static constexpr int TILE = 1024;      // particles per tile / thread block
 static constexpr int TPB = 256;        // threads per block in tile kernels
 static constexpr int IPT = TILE / TPB; // items per thread (k_cm_tile: consecutive; flag/scatter passes: striped i = base + j*TPB + t)
-static_assert(IPT == 4, "k_cm_tile loads node ids as int4");
 static constexpr int SMAX = 32;        // node runs per tile accumulated in shared memory
 
 // ---- helpers ---------------------------------------------------------------------------------
@@ -177,31 +176,38 @@ __device__ __forceinline__ void flush_part(const Part &p, int nd, int n0, Slot *
   }
 }
 
-// Each thread owns IPT CONSECUTIVE particles, so a warp covers 128 consecutive particles = one or two nodes at
-// any depth; per-thread partials are combined by a segmented warp scan keyed on the node id (ids are
-// non-decreasing along the array), and only the last lane of each run touches the accumulators.  (The first
-// version striped the items over the block; at deep levels nearly every warp then straddled several nodes and
-// fell back to per-thread shared-memory atomics -- k_cm_tile was 55 % of the build, profiles/r1_launches_summary.md.)
-__device__ __forceinline__ void part_merge(Part &a, const Part &b) {
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { a.umin[k] = min(a.umin[k], b.umin[k]); a.umax[k] = max(a.umax[k], b.umax[k]); }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) a.s[k] += b.s[k];
-}
-__device__ __forceinline__ Part part_shfl_up(const Part &p, int o) {
-  Part q;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { q.umin[k] = __shfl_up_sync(0xffffffffu, p.umin[k], o); q.umax[k] = __shfl_up_sync(0xffffffffu, p.umax[k], o); }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) q.s[k] = __shfl_up_sync(0xffffffffu, p.s[k], o);
-  return q;
+// A warp owns CM_IPT rows of 32 consecutive particles (coalesced 128-byte node-id and 512-byte record loads, CM_IPT of
+// each in flight per lane).  Node ids are non-decreasing along the array, so those 32*CM_IPT particles are one to three
+// runs; for each distinct node in turn (a warp-uniform loop) every lane sums its particles of that node, the 32 partials
+// are combined by a plain warp reduction -- REDUX for the six box bounds, a shuffle tree for the four 64-bit sums -- and
+// lane 0 adds the result to the block's shared-memory slot of the node.  (The first version striped items over the
+// block and fell back to per-thread shared atomics; the second combined per-thread partials of 4 consecutive
+// particles with a 14-word segmented warp scan -- 75 shuffles per 128 particles, issue-bound at 35 % of the HBM peak,
+// profiles/r1j_build_ncu_summary.md.)
+static constexpr int CM_IPT = 8;
+static constexpr int CM_TILE = TPB * CM_IPT;
+
+__device__ __forceinline__ long long shfl_xor_ll(long long v, int o) {
+  int lo = __shfl_xor_sync(0xffffffffu, (int)(unsigned)(v & 0xffffffffll), o);
+  int hi = __shfl_xor_sync(0xffffffffu, (int)(v >> 32), o);
+  return ((long long)hi << 32) | (long long)(unsigned)lo;
 }
 
 __global__ void __launch_bounds__(TPB) k_cm_tile(const float4 *__restrict__ rec, const int *__restrict__ nid, int n,
                                                  NodeAcc *__restrict__ acc, const float *__restrict__ scales) {
   __shared__ int s_n0;
   __shared__ Slot slots[SMAX];
-  const int t = threadIdx.x, lane = t & 31, base = blockIdx.x * TILE;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int wbase = blockIdx.x * CM_TILE + w * (32 * CM_IPT) + lane;
+  int nd[CM_IPT];
+  float4 r[CM_IPT];
+#pragma unroll
+  for (int k = 0; k < CM_IPT; ++k) {
+    const int i = wbase + 32 * k;
+    nd[k] = (i < n) ? __ldcs(nid + i) : -1;
+  }
+#pragma unroll
+  for (int k = 0; k < CM_IPT; ++k) if (nd[k] >= 0) r[k] = __ldcs(rec + wbase + 32 * k);
   if (t == 0) s_n0 = INT_MAX;
   if (t < SMAX) {
     Slot &S = slots[t];
@@ -209,47 +215,34 @@ __global__ void __launch_bounds__(TPB) k_cm_tile(const float4 *__restrict__ rec,
     S.used = 0; S.s[0] = S.s[1] = S.s[2] = S.s[3] = 0;
   }
   __syncthreads();
-  const int i0 = base + IPT * t;
-  int nd[IPT];
-  if (i0 + IPT <= n) {
-    const int4 v = *reinterpret_cast<const int4 *>(nid + i0);
-    nd[0] = v.x; nd[1] = v.y; nd[2] = v.z; nd[3] = v.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) nd[j] = (i0 + j < n) ? nid[i0 + j] : -1;
-  }
   int mn = INT_MAX;
 #pragma unroll
-  for (int j = 0; j < IPT; ++j) if (nd[j] >= 0) mn = min(mn, nd[j]);
-  mn = __reduce_min_sync(0xffffffffu, mn);
+  for (int k = 0; k < CM_IPT; ++k) if (nd[k] >= 0) mn = min(mn, nd[k]);
+  mn = __reduce_min_sync(0xffffffffu, mn);       // the warp's first node
   if (lane == 0 && mn != INT_MAX) atomicMin(&s_n0, mn);
   __syncthreads();
   const int n0 = s_n0;
   if (n0 == INT_MAX) return;   // no active particle in this tile
   const float sx = scales[0], sm = scales[1];
-
-  // per-thread run: the node of the thread's last active particle; particles of other nodes (a node boundary
-  // inside the thread's four) are flushed on their own
-  int key = -1;
+  int key = mn;
+  while (key != INT_MAX) {     // warp-uniform: one pass per distinct node among the warp's particles
+    Part p; part_reset(p);
+    int next = INT_MAX;
 #pragma unroll
-  for (int j = 0; j < IPT; ++j) if (nd[j] >= 0) key = nd[j];
-  Part p; part_reset(p);
+    for (int k = 0; k < CM_IPT; ++k) {
+      if (nd[k] == key) part_add(p, r[k], sx, sm);
+      else if (nd[k] > key) next = min(next, nd[k]);
+    }
 #pragma unroll
-  for (int j = 0; j < IPT; ++j) {
-    if (nd[j] < 0) continue;
-    const float4 r = rec[i0 + j];
-    if (nd[j] == key) part_add(p, r, sx, sm);
-    else { Part q; part_reset(q); part_add(q, r, sx, sm); flush_part(q, nd[j], n0, slots, acc); }
+    for (int q = 0; q < 3; ++q) { p.umin[q] = __reduce_min_sync(0xffffffffu, p.umin[q]); p.umax[q] = __reduce_max_sync(0xffffffffu, p.umax[q]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) p.s[q] += shfl_xor_ll(p.s[q], o);
+    }
+    if (lane == 0) flush_part(p, key, n0, slots, acc);
+    key = __reduce_min_sync(0xffffffffu, next);
   }
-  // segmented inclusive scan over the warp; finished particles (key -1) form their own runs and are dropped
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const Part q = part_shfl_up(p, o);
-    const int okey = __shfl_up_sync(0xffffffffu, key, o);
-    if (lane >= o && okey == key) part_merge(p, q);
-  }
-  const int nkey = __shfl_down_sync(0xffffffffu, key, 1);
-  if (key >= 0 && (lane == 31 || nkey != key)) flush_part(p, key, n0, slots, acc);
   __syncthreads();
   if (t < SMAX && slots[t].used) {
     NodeAcc &A = acc[n0 + t];
@@ -327,32 +320,51 @@ __global__ void __launch_bounds__(256) k_level_children(Node *__restrict__ nodes
 }
 
 // ---- shared by C1 and C3: left flags of a tile and their exclusive prefix in particle order --------------
-struct ItemInfo { int nd, sp, flag, excl; };
+struct ItemInfo { int sp, flag, excl, offset, count, cl, cr; };
 
-__device__ __forceinline__ int tile_flags_scan(const float4 *__restrict__ rec, const int *__restrict__ nid,
-                                               const Node *__restrict__ nodes, int n, int base, ItemInfo it[IPT],
-                                               float4 r[IPT], bool load_rec, int *s_w) {
-  // Particle i = base + j*TPB + t: in particle order the tile is IPT rows of TPB/32 warps.  One ballot per (row, warp)
-  // gives the left count of 32 consecutive particles; the IPT*TPB/32 = 32 counts are scanned by one warp -- a single
-  // barrier pair instead of IPT block-wide scans.
+// striped tile layout of the flag passes: particle i = tile*TILE + j*TPB + t
+__device__ __forceinline__ void st_load_nid(const int *__restrict__ nid, int n, int tile, int ntiles, int nd[IPT]) {
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) {
+    const int i = tile * TILE + j * TPB + (int)threadIdx.x;
+    nd[j] = (tile < ntiles && i < n) ? __ldcs(nid + i) : -1;
+  }
+}
+__device__ __forceinline__ void st_load_rec(const float4 *__restrict__ rec, int tile, const int nd[IPT], float4 r[IPT]) {
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) if (nd[j] >= 0) r[j] = __ldcs(rec + tile * TILE + j * TPB + (int)threadIdx.x);
+}
+__device__ __forceinline__ void st_load_idx(const unsigned *__restrict__ idx, int tile, const int nd[IPT], unsigned x[IPT]) {
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) if (nd[j] >= 0) x[j] = __ldcs(idx + tile * TILE + j * TPB + (int)threadIdx.x);
+}
+
+__device__ __forceinline__ int tile_flags_scan(const Node *__restrict__ nodes, const int nd[IPT], const float4 r[IPT],
+                                               ItemInfo it[IPT], int *s_w) {
+  // In particle order the tile is IPT rows of TPB/32 warps.  One ballot per (row, warp) gives the left count of 32
+  // consecutive particles; the IPT*TPB/32 = 32 counts are scanned by one warp -- a single barrier pair instead of IPT
+  // block-wide scans.  The node's metadata comes in three independent 16-byte loads (no load depends on the split
+  // dimension read by another).
   static_assert(IPT * (TPB / 32) == 32, "one warp scans the per-(row, warp) counts");
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   unsigned bal[IPT];
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
-    int i = base + j * TPB + t;
-    int nd = (i < n) ? nid[i] : -1;
     int sp = -1, flag = 0;
-    if (nd >= 0) {
-      sp = __ldg(&nodes[nd].split);
-      if (load_rec) r[j] = rec[i];
+    it[j].offset = 0; it[j].count = 0; it[j].cl = 0; it[j].cr = 0;
+    if (nd[j] >= 0) {
+      const float4 *np = reinterpret_cast<const float4 *>(nodes + nd[j]);
+      const float4 a = __ldg(np), c = __ldg(np + 2), d = __ldg(np + 3);
+      sp = __float_as_int(d.w);
+      it[j].count = __float_as_int(a.x); it[j].offset = __float_as_int(a.y);
+      it[j].cl = __float_as_int(a.z); it[j].cr = __float_as_int(a.w);
       if (sp >= 0) {
-        float key = load_rec ? comp(r[j], sp) : reinterpret_cast<const float *>(rec)[4 * (size_t)i + sp];
-        flag = key < __ldg(&nodes[nd].xc[sp]);                         // RCBForceTree.cxx:640, pivot :720
+        const float pivot = sp == 0 ? c.z : (sp == 1 ? c.w : d.x);             // xc[sp], RCBForceTree.cxx:720
+        flag = comp(r[j], sp) < pivot;                                         // :640
       }
     }
     bal[j] = __ballot_sync(0xffffffffu, flag);
-    it[j].nd = nd; it[j].sp = sp; it[j].flag = flag;
+    it[j].sp = sp; it[j].flag = flag;
     if (lane == 0) s_w[j * (TPB / 32) + w] = __popc(bal[j]);
   }
   __syncthreads();
@@ -373,23 +385,34 @@ __device__ __forceinline__ int tile_flags_scan(const float4 *__restrict__ rec, c
 }
 
 __global__ void __launch_bounds__(TPB) k_left_count(const float4 *__restrict__ rec, const int *__restrict__ nid,
-                                                    const Node *__restrict__ nodes, int n,
+                                                    const Node *__restrict__ nodes, int n, int ntiles,
                                                     unsigned *__restrict__ tilecount, int *__restrict__ lstart,
                                                     int *__restrict__ lend) {
-  __shared__ int s_w[34];
-  ItemInfo it[IPT]; float4 r[IPT];
-  const int base = blockIdx.x * TILE;
-  int total = tile_flags_scan(rec, nid, nodes, n, base, it, r, false, s_w);
+  __shared__ int s_w[2][34];     // alternating per iteration: a slow warp may still read the previous tile's prefixes
+  const int stride = gridDim.x;
+  int nd[IPT], nd1[IPT], nd2[IPT];
+  float4 r[IPT], r1[IPT];
+  ItemInfo it[IPT];
+  int tile = blockIdx.x;
+  st_load_nid(nid, n, tile, ntiles, nd);
+  st_load_nid(nid, n, tile + stride, ntiles, nd1);
+  st_load_rec(rec, tile, nd, r);
+  for (int k = 0; tile < ntiles; tile += stride, ++k) {
+    st_load_nid(nid, n, tile + 2 * stride, ntiles, nd2);
+    st_load_rec(rec, tile + stride, nd1, r1);
+    const int total = tile_flags_scan(nodes, nd, r, it, s_w[k & 1]);
 #pragma unroll
-  for (int j = 0; j < IPT; ++j) {
-    if (it[j].sp >= 0) {
-      int i = base + j * TPB + threadIdx.x;
-      int off = nodes[it[j].nd].offset, cnt = nodes[it[j].nd].count;
-      if (i == off) lstart[it[j].nd] = it[j].excl;
-      if (i == off + cnt - 1) lend[it[j].nd] = it[j].excl + it[j].flag;
+    for (int j = 0; j < IPT; ++j) {
+      if (it[j].sp >= 0) {
+        const int i = tile * TILE + j * TPB + (int)threadIdx.x;
+        if (i == it[j].offset) lstart[nd[j]] = it[j].excl;
+        if (i == it[j].offset + it[j].count - 1) lend[nd[j]] = it[j].excl + it[j].flag;
+      }
     }
+    if (threadIdx.x == 0) tilecount[tile] = (unsigned)total;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) { nd[j] = nd1[j]; nd1[j] = nd2[j]; r[j] = r1[j]; }
   }
-  if (threadIdx.x == 0) tilecount[blockIdx.x] = (unsigned)total;
 }
 
 // single-block exclusive scan (n up to a few million; used on per-tile and per-node counts)
@@ -433,32 +456,53 @@ __global__ void k_set_children(Node *__restrict__ nodes, int begin, int end, con
 
 __global__ void __launch_bounds__(TPB) k_scatter(const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
                                                  const int *__restrict__ nid, const Node *__restrict__ nodes, int n,
-                                                 const unsigned *__restrict__ tilebase, const int *__restrict__ lbase,
-                                                 const int *__restrict__ nleft, float4 *__restrict__ rec_out,
-                                                 unsigned *__restrict__ idx_out, int *__restrict__ nid_out,
-                                                 float4 *__restrict__ src4, unsigned *__restrict__ perm) {
-  __shared__ int s_w[34];
-  ItemInfo it[IPT]; float4 r[IPT];
-  const int base = blockIdx.x * TILE;
-  tile_flags_scan(rec, nid, nodes, n, base, it, r, true, s_w);
-  const int tb = (int)tilebase[blockIdx.x];
+                                                 int ntiles, const unsigned *__restrict__ tilebase,
+                                                 const int *__restrict__ lbase, const int *__restrict__ nleft,
+                                                 float4 *__restrict__ rec_out, unsigned *__restrict__ idx_out,
+                                                 int *__restrict__ nid_out, float4 *__restrict__ src4,
+                                                 unsigned *__restrict__ perm) {
+  __shared__ int s_w[2][34];
+  const int stride = gridDim.x;
+  int nd[IPT], nd1[IPT], nd2[IPT];
+  float4 r[IPT], r1[IPT];
+  unsigned ix[IPT], ix1[IPT];
+  ItemInfo it[IPT];
+  int tile = blockIdx.x;
+  st_load_nid(nid, n, tile, ntiles, nd);
+  st_load_nid(nid, n, tile + stride, ntiles, nd1);
+  st_load_rec(rec, tile, nd, r);
+  st_load_idx(idx, tile, nd, ix);
+  for (int k = 0; tile < ntiles; tile += stride, ++k) {
+    st_load_nid(nid, n, tile + 2 * stride, ntiles, nd2);
+    st_load_rec(rec, tile + stride, nd1, r1);
+    st_load_idx(idx, tile + stride, nd1, ix1);
+    // per-node split bookkeeping of this tile's particles: independent of the flag scan, issued before its barriers
+    int nl[IPT], lb[IPT];
 #pragma unroll
-  for (int j = 0; j < IPT; ++j) {
-    int i = base + j * TPB + threadIdx.x;
-    if (i >= n) continue;
-    int nd = it[j].nd;
-    if (nd < 0) { nid_out[i] = -1; continue; }
-    int sp = it[j].sp;
-    if (sp < 0 || nleft[nd] < 0) {   // finished leaf (or degenerate split): final position reached
-      src4[i] = r[j]; perm[i] = idx[i]; nid_out[i] = -1;
-      continue;
+    for (int j = 0; j < IPT; ++j) {
+      nl[j] = 0; lb[j] = 0;
+      if (nd[j] >= 0) { nl[j] = __ldg(nleft + nd[j]); lb[j] = __ldg(lbase + nd[j]); }
     }
-    int off = nodes[nd].offset;
-    int L = tb + it[j].excl - lbase[nd];       // left flags of this node before i
-    int dest, child;
-    if (it[j].flag) { dest = off + L; child = nodes[nd].cl; }
-    else { dest = off + nleft[nd] + ((i - off) - L); child = nodes[nd].cr; }
-    rec_out[dest] = r[j]; idx_out[dest] = idx[i]; nid_out[dest] = child;
+    const int tb = (int)tilebase[tile];
+    tile_flags_scan(nodes, nd, r, it, s_w[k & 1]);
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      const int i = tile * TILE + j * TPB + (int)threadIdx.x;
+      if (i >= n) continue;
+      if (nd[j] < 0) { nid_out[i] = -1; continue; }
+      if (it[j].sp < 0 || nl[j] < 0) {   // finished leaf (or degenerate split): final position reached
+        src4[i] = r[j]; perm[i] = ix[j]; nid_out[i] = -1;
+        continue;
+      }
+      const int off = it[j].offset;
+      const int L = tb + it[j].excl - lb[j];       // left flags of this node before i
+      int dest, child;
+      if (it[j].flag) { dest = off + L; child = it[j].cl; }
+      else { dest = off + nl[j] + ((i - off) - L); child = it[j].cr; }
+      rec_out[dest] = r[j]; idx_out[dest] = ix[j]; nid_out[dest] = child;
+    }
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) { nd[j] = nd1[j]; nd1[j] = nd2[j]; r[j] = r1[j]; ix[j] = ix1[j]; }
   }
 }
 
@@ -620,9 +664,71 @@ __global__ void __launch_bounds__(256) k_gather(Soa in, Soa out, const float4 *_
 }
 
 // ---- host orchestration -------------------------------------------------------------------------------
+// Long inputs (per-particle flags: the out-of-box compaction, the refresh classification) are scanned in three launches:
+// per-block sums of 2048 elements, the single-block scan above over those sums, per-block scan + base.  The single-block
+// kernel alone walks the array 1024 elements at a time: 60 ms for the 152 M flags of a 512^3 sub-volume.
+static constexpr int SCAN_TPB = 256, SCAN_IPT = 8, SCAN_TILE = SCAN_TPB * SCAN_IPT;
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_reduce(const unsigned *__restrict__ in, long long n,
+                                                           unsigned *__restrict__ blocksum) {
+  __shared__ unsigned s_w[SCAN_TPB / 32];
+  const long long i0 = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_IPT;
+  unsigned v = 0;
+  if (i0 + SCAN_IPT <= n) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(in + i0), b = *reinterpret_cast<const uint4 *>(in + i0 + 4);
+    v = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  } else {
+    for (int j = 0; j < SCAN_IPT; ++j) if (i0 + j < n) v += in[i0 + j];
+  }
+  v = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < SCAN_TPB / 32; ++w) t += s_w[w];
+    blocksum[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_apply(const unsigned *__restrict__ in, unsigned *__restrict__ out,
+                                                          long long n, const unsigned *__restrict__ blockbase) {
+  __shared__ int s_w[34];
+  const long long i0 = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_IPT;
+  unsigned v[SCAN_IPT];
+  if (i0 + SCAN_IPT <= n) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(in + i0), b = *reinterpret_cast<const uint4 *>(in + i0 + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < SCAN_IPT; ++j) v[j] = (i0 + j < n) ? in[i0 + j] : 0u;
+  }
+  unsigned t = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_IPT; ++j) { const unsigned x = v[j]; v[j] = t; t += x; }
+  int total;
+  const unsigned base = blockbase[blockIdx.x] + (unsigned)block_excl_scan((int)t, s_w, &total);
+  if (i0 + SCAN_IPT <= n) {
+    *reinterpret_cast<uint4 *>(out + i0) = make_uint4(base + v[0], base + v[1], base + v[2], base + v[3]);
+    *reinterpret_cast<uint4 *>(out + i0 + 4) = make_uint4(base + v[4], base + v[5], base + v[6], base + v[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < SCAN_IPT; ++j) if (i0 + j < n) out[i0 + j] = base + v[j];
+  }
+}
+
 int scan_exclusive(haccsr_ctx *c, const unsigned *in, unsigned *out, int64_t n, unsigned long long *d_total) {
-  k_scan<<<1, 1024, 0, c->stream>>>(in, out, (long long)n, d_total);
-  c->launches++;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  if (n < 16 * SCAN_TILE || !aligned) {
+    k_scan<<<1, 1024, 0, c->stream>>>(in, out, (long long)n, d_total);
+    c->launches++;
+    HSR_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const int64_t nblk = (n + SCAN_TILE - 1) / SCAN_TILE;
+  HSR_TRY(c->scan_tmp.ensure(2 * (size_t)nblk + 2));
+  unsigned *bsum = c->scan_tmp.p, *bbase = c->scan_tmp.p + nblk + 1;
+  k_scan_reduce<<<(unsigned)nblk, SCAN_TPB, 0, c->stream>>>(in, (long long)n, bsum);
+  k_scan<<<1, 1024, 0, c->stream>>>(bsum, bbase, (long long)nblk, d_total);
+  k_scan_apply<<<(unsigned)nblk, SCAN_TPB, 0, c->stream>>>(in, out, (long long)n, bbase);
+  c->launches += 3;
   HSR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -634,6 +740,15 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
   const int ppn = (int)(ppn64 > INT_MAX ? INT_MAX : ppn64);
   cudaStream_t st = c->stream;
   const int ntiles = (n + TILE - 1) / TILE;
+  // persistent grids of the tile kernels: as many blocks as are resident at once, each walking tiles with stride gridDim
+  static int occ_lc = 0, occ_sc = 0;
+  if (!occ_lc) {
+    HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sc, k_scatter, TPB, 0));
+    HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lc, k_left_count, TPB, 0));
+    if (occ_lc < 1 || occ_sc < 1) { occ_lc = 0; set_error("tile kernels do not fit on an SM"); return 2; }
+  }
+  const int grid_lc = ntiles < c->sm_count * occ_lc ? (ntiles > 0 ? ntiles : 1) : c->sm_count * occ_lc;
+  const int grid_sc = ntiles < c->sm_count * occ_sc ? (ntiles > 0 ? ntiles : 1) : c->sm_count * occ_sc;
   // node pool: every split node has > ppn particles and two non-empty children, so nodes <= 2N-1; in
   // practice ~4N/ppn.  Start generously and grow (rebuild) if the pool runs out.
   int64_t want_nodes = 1024 + 8 * (n64 / (ppn > 0 ? ppn : 1));
@@ -680,7 +795,7 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
     for (;; ++level) {
       if (level >= 127) { set_error("tree deeper than 127 levels"); return 1; }
       c->level_begin[level] = begin; c->level_end[level] = end;
-      k_cm_tile<<<ntiles, TPB, 0, st>>>(rec, nid, n, c->acc.p, scales);
+      k_cm_tile<<<(n + CM_TILE - 1) / CM_TILE, TPB, 0, st>>>(rec, nid, n, c->acc.p, scales);
       {
         const int nl = end - begin, gb = (nl + 255) / 256;
         HSR_TRY(c->split_flag.ensure((size_t)nl + 1)); HSR_TRY(c->split_rank.ensure((size_t)nl + 1));
@@ -696,7 +811,7 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
       if (level == 0) c->unit_mass = li.unit_mass != 0;
       if (li.error) { overflow = true; break; }
       if (li.nsplit > 0) {
-        k_left_count<<<ntiles, TPB, 0, st>>>(rec, nid, c->nodes.p, n, c->tilecount.p, c->lstart.p, c->lend.p);
+        k_left_count<<<grid_lc, TPB, 0, st>>>(rec, nid, c->nodes.p, n, ntiles, c->tilecount.p, c->lstart.p, c->lend.p);
         c->launches++;
         HSR_TRY(scan_exclusive(c, c->tilecount.p, c->tilebase.p, ntiles, nullptr));
         int nl = end - begin;
@@ -704,7 +819,7 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
                                                           c->lend.p, c->lbase.p, c->nleft.p);
         c->launches++;
       }
-      k_scatter<<<ntiles, TPB, 0, st>>>(rec, idx, nid, c->nodes.p, n, c->tilebase.p, c->lbase.p, c->nleft.p, rec_o,
+      k_scatter<<<grid_sc, TPB, 0, st>>>(rec, idx, nid, c->nodes.p, n, ntiles, c->tilebase.p, c->lbase.p, c->nleft.p, rec_o,
                                         idx_o, nid_o, c->src4.p, c->perm.p);
       c->launches++;
       HSR_CUDA(cudaGetLastError());

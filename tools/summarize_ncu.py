@@ -1,54 +1,89 @@
-#!/usr/bin/env python
-"""Turn `ncu -i X.ncu-rep --page raw --csv` of one kernel launch into a short markdown table of the metrics
-that matter for an FMA-pipe- or HBM-bound kernel.
-    ncu -i gpurun_out/x.ncu-rep --page raw --csv > /tmp/x.csv
-    python tools/summarize_ncu.py /tmp/x.csv "title" [pairs_in_launch] > profiles/x_summary.md
-"""
-import csv
-import sys
+"""Summarise an `ncu --set full` report (.ncu-rep) as a markdown table, one column per kernel (mean over its launches).
 
-WANT = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second",
-        "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
-        "launch__occupancy_limit_blocks", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
-        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
-        "smsp__thread_inst_executed_per_inst_executed.ratio",
-        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+  python tools/summarize_ncu.py gpurun_out/r1j_build.ncu-rep --title "..." > profiles/r1j_build_ncu_summary.md
+  python tools/summarize_ncu.py REP --traffic k_force      # prints DRAM bytes per launch (for profiles/traffic.json)
+"""
+import argparse
+import collections
+import csv
+import io
+import re
+import subprocess
+
+METRICS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+]
+SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+
+
+def load(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    return rows[0], rows[1], rows[2:]
+
+
+def short(name):
+    return re.sub(r"\(.*", "", name).replace("void ", "").strip()
 
 
 def main():
-    path, title = sys.argv[1], sys.argv[2]
-    pairs = float(sys.argv[3]) if len(sys.argv) > 3 else None
-    row = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-    rows = list(csv.reader(open(path)))
-    hdr, units, vals = rows[0], rows[1], rows[2 + row]
-    d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
-    print("# %s\n" % title)
-    print("| metric | unit | value |\n|---|---|---|")
-    for w in WANT:
-        if w in d:
-            print("| %s | %s | %s |" % (w, d[w][0], d[w][1]))
-    if pairs:
-        t = float(d["gpu__time_duration.sum"][1].replace(",", "")) * {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}[d["gpu__time_duration.sum"][0]]
-        inst = float(d["smsp__inst_executed.sum"][1].replace(",", ""))
-        print("\nDerived: %.3e pairs in this launch -> %.3f T pairs/s under the profiler = %.1f TFLOP/s at 30 flop/pair = "
-              "%.1f %% of the 74.45 TFLOP/s FP32 peak; %.1f warp instructions per warp-pair (32 sinks x 1 source)." % (
-                  pairs, pairs / t / 1e12, 30 * pairs / t / 1e12, 100 * 30 * pairs / t / 74.45e12, inst / (pairs / 32)))
+    ap = argparse.ArgumentParser()
+    ap.add_argument("report")
+    ap.add_argument("--title", default=None)
+    ap.add_argument("--traffic", default=None, help="kernel name prefix: print mean DRAM bytes per launch")
+    a = ap.parse_args()
+    hdr, units, rows = load(a.report)
+    col = {h: i for i, h in enumerate(hdr)}
+    groups = collections.OrderedDict()
+    for r in rows:
+        groups.setdefault(short(r[col["Kernel Name"]]), []).append(r)
+
+    def mean(rs, m):
+        i = col.get(m)
+        if i is None:
+            return None
+        vals = [float(r[i].replace(",", "")) for r in rs if r[i] not in ("", "n/a")]
+        if not vals:
+            return None
+        return sum(vals) / len(vals) * SCALE.get(units[i], 1.0)
+
+    if a.traffic:
+        for k, rs in groups.items():
+            if k.startswith(a.traffic):
+                print(int(mean(rs, "dram__bytes_read.sum") + mean(rs, "dram__bytes_write.sum")))
+        return
+    names = list(groups)
+    print("# %s" % (a.title or a.report))
+    print()
+    print("Means over the captured launches of each kernel (`ncu --set full --clock-control none`); times in us, bytes in B.")
+    print()
+    print("| metric | " + " | ".join("%s (x%d)" % (k, len(groups[k])) for k in names) + " |")
+    print("|---|" + "---:|" * len(names))
+    for m in METRICS:
+        vals = [mean(groups[k], m) for k in names]
+        if all(v is None for v in vals):
+            continue
+        print("| %s | " % m + " | ".join("-" if v is None else ("%.4g" % v) for v in vals) + " |")
+    print()
+    print("| derived | " + " | ".join(names) + " |")
+    print("|---|" + "---:|" * len(names))
+    bw = []
+    for k in names:
+        t = mean(groups[k], "gpu__time_duration.sum")
+        b = (mean(groups[k], "dram__bytes_read.sum") or 0) + (mean(groups[k], "dram__bytes_write.sum") or 0)
+        bw.append("%.0f" % (b / (t * 1e-6) / 1e9) if t else "-")
+    print("| DRAM GB/s (read+write bytes / duration) | " + " | ".join(bw) + " |")
 
 
 if __name__ == "__main__":
