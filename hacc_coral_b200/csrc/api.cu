@@ -4,6 +4,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -136,6 +137,7 @@ int haccsr_create(haccsr_ctx **out, int device, int64_t max_particles) {
   haccsr_ctx *c = new (std::nothrow) haccsr_ctx();
   if (!c) { set_error("out of host memory"); return 2; }
   c->device = device; c->sm_count = prop.multiProcessorCount; c->cap = max_particles;
+  if (const char *e = getenv("HACCSR_ITEM_POLICY")) c->item_policy = atoi(e) & 1;
   int rc = 0;
   do {
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = 2; break; }

@@ -95,7 +95,8 @@ struct LevelInfo {
   int unit_mass;      // written with the root: 1 = every particle mass is exactly 1.0f
 };
 
-struct WorkItem { int node, sink_begin, sink_count, no_pseudo; };   // no_pseudo: the node's list holds real particles only
+// no_pseudo bit 0: the node's list holds real particles only; bit 1: remainder item (sources over lanes, force.cu)
+struct WorkItem { int node, sink_begin, sink_count, no_pseudo; };
 
 }  // namespace haccsr
 
@@ -147,6 +148,7 @@ struct haccsr_ctx {
   haccsr::DevBuf<haccsr::WorkItem> items, items_sorted;   // in node order; sorted by decreasing work
   haccsr::DevBuf<unsigned> lpt_hist;
   int64_t n_items = 0;
+  int item_policy = 1;   // force.cu leaf_cut: 1 = remainder items, 0 = padded groups only (env HACCSR_ITEM_POLICY, for A/B measurements)
 
   // PM coupling (cic.cu): fixed-point deposit accumulators and a staging copy of the grid
   haccsr::DevBuf<unsigned long long> cic_acc;
@@ -170,7 +172,7 @@ struct haccsr_ctx {
   const void *pending_ho = nullptr;   // host output arrays whose device->host copies are not queued yet (api.cu)
   int64_t pending_count = 0;
   int force_groups = 1;
-  int64_t group_off[9] = {0};
+  int64_t seg_off[17] = {0};          // item ranges of the launches: (group g, chunk items) = [2g, 2g+1), remainder items [2g+1, 2g+2)
   float *ho_v[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int launches = 0, force_launches = 0;

@@ -382,6 +382,127 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
   }
 }
 
+// Remainder items (kernel k_force_rem): the last r = count mod 32 sinks of a leaf (r <= REM_MAX).  As one more group of
+// 32 sinks they would occupy a whole warp for the whole list with r/32 of the lanes doing useful work (a 328-particle
+// leaf: 11 groups for 10.25 groups of sinks, 7 % of the kernel).  Here the roles are swapped: SOURCES are spread over the
+// lanes, every lane holds the same REM_SINKS sinks, and the list is streamed once per batch of REM_SINKS sinks --
+// ceil(r/8)/4 of a group's time.  A warp then consumes a 128-source tile in four iterations, so the kernel has its own,
+// deeper ring (REM_STAGES tiles in flight per warp) and runs as a separate launch: the main kernel's code and register
+// budget stay what they were.  Each lane accumulates the sources j = lane (mod 32) of every tile in list order; the 32
+// partial sums of a sink are combined by a fixed xor-shuffle tree, so the result is deterministic (reduction order for
+// the parity gate: 32 interleaved sequential sums, then the tree; all other sinks keep one sequential sum).
+static constexpr int REM_SINKS = 8;     // sinks per batch (four packed pairs)
+static constexpr int REM_MAX = 24;      // r > REM_MAX: four batches cost as much as a padded group
+static constexpr int REM_STAGES = 8;    // ring depth of k_force_rem
+static constexpr int ITEM_REM = 2;      // WorkItem::no_pseudo bit 1
+
+struct ProducerRep { Producer pr; unsigned first_ri, total, passes_left; };
+// lane 0 only: next tile of a list that is streamed `passes` times; a tile never straddles two passes
+__device__ __noinline__ void produce_tile_rep(ProducerRep &q, const ForceParams &P, float4 *tile, unsigned bar) {
+  if (q.pr.remaining == 0) {
+    if (q.passes_left == 0) return;
+    q.passes_left--;
+    q.pr.ri = q.first_ri; q.pr.roff = 0; q.pr.remaining = q.total;
+  }
+  produce_tile(q.pr, P, tile, bar);
+}
+
+template <int NST, int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM, int FUSED>
+__device__ __forceinline__ void run_item_rem(const WorkItem it, const ForceParams &P, float4 (*tiles)[FTILE],
+                                             unsigned long long *bars) {
+  constexpr int S2 = REM_SINKS / 2;
+  const int lane = threadIdx.x;
+  const unsigned total = P.list_len[it.node];
+  const unsigned ntiles = (total + FTILE - 1) / FTILE;
+  const int nbatch = (it.sink_count + REM_SINKS - 1) / REM_SINKS;
+  ProducerRep q;
+  q.pr.ranges = P.ranges; q.first_ri = P.range_off[it.node]; q.pr.rend = P.range_off[it.node + 1];
+  q.pr.ri = q.first_ri; q.pr.roff = 0; q.pr.remaining = 0; q.total = total; q.passes_left = (unsigned)nbatch;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) produce_tile_rep(q, P, tiles[s], smem_u32(&bars[s]));
+  }
+  unsigned T = 0;                      // tiles consumed so far over all batches: ring stage and mbarrier parity
+  unsigned long long c64 = 0, f64 = 0;
+  for (int b = 0; b < nbatch; ++b) {
+    SinkRegs2 k2[S2];
+#pragma unroll
+    for (int g = 0; g < REM_SINKS; ++g) {
+      const int j = b * REM_SINKS + g;   // sinks past the end re-use the item's first sink (result discarded)
+      const float4 s = __ldg(P.src4 + it.sink_begin + (j < it.sink_count ? j : 0));
+      SinkRegs2 &k = k2[g >> 1];
+      if ((g & 1) == 0) { k.nx.x = -s.x; k.ny.x = -s.y; k.nz.x = -s.z; }
+      else { k.nx.y = -s.x; k.ny.y = -s.y; k.nz.y = -s.z; }
+    }
+#pragma unroll
+    for (int k = 0; k < S2; ++k) k2[k].ax = k2[k].ay = k2[k].az = make_float2(0.f, 0.f);
+    unsigned cnt[REM_SINKS], nf[REM_SINKS];
+#pragma unroll
+    for (int g = 0; g < REM_SINKS; ++g) { cnt[g] = 0; nf[g] = 0; }
+    for (unsigned t = 0; t < ntiles; ++t, ++T) {
+      const int stage = T % NST;
+      const unsigned parity = (T / NST) & 1u;
+      mbar_wait(smem_u32(&bars[stage]), parity);
+      const unsigned nsrc = (t + 1 == ntiles) ? (total - t * FTILE) : (unsigned)FTILE;
+      const float4 *tile = tiles[stage];
+#pragma unroll 1
+      for (unsigned j0 = 0; j0 < nsrc; j0 += 32) {
+        const bool valid = j0 + lane < nsrc;
+        // lanes past the end of the list see a source far outside every cutoff (finite r2, predicate false)
+        const float4 s = valid ? tile[j0 + lane] : make_float4(3.0e15f, 3.0e15f, 3.0e15f, 0.f);
+#pragma unroll
+        for (int k = 0; k < S2; ++k) {
+          if (FUSED == 2) {
+            unsigned na = 0, nb = 0;
+            interact2_cull<NC, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1], na, nb);
+            if (COUNT && valid) { nf[2 * k] += na; nf[2 * k + 1] += nb; }
+          } else if (FUSED) interact2_fused<NC, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
+          else interact2<NC, LAW, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
+        }
+      }
+      __syncwarp();                       // every lane is done reading this stage
+      if (lane == 0) produce_tile_rep(q, P, tiles[stage], smem_u32(&bars[stage]));
+    }
+    // the 32 partial sums of every sink: fixed xor tree, every lane ends up with the total
+#pragma unroll
+    for (int k = 0; k < S2; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        k2[k].ax.x = __fadd_rn(k2[k].ax.x, __shfl_xor_sync(0xffffffffu, k2[k].ax.x, o));
+        k2[k].ax.y = __fadd_rn(k2[k].ax.y, __shfl_xor_sync(0xffffffffu, k2[k].ax.y, o));
+        k2[k].ay.x = __fadd_rn(k2[k].ay.x, __shfl_xor_sync(0xffffffffu, k2[k].ay.x, o));
+        k2[k].ay.y = __fadd_rn(k2[k].ay.y, __shfl_xor_sync(0xffffffffu, k2[k].ay.y, o));
+        k2[k].az.x = __fadd_rn(k2[k].az.x, __shfl_xor_sync(0xffffffffu, k2[k].az.x, o));
+        k2[k].az.y = __fadd_rn(k2[k].az.y, __shfl_xor_sync(0xffffffffu, k2[k].az.y, o));
+      }
+    }
+    // kick: lane g writes sink g of the batch   (RCBForceTree.cxx:594-596 / :615-617)
+    float ax = k2[0].ax.x, ay = k2[0].ay.x, az = k2[0].az.x;
+#pragma unroll
+    for (int g = 1; g < REM_SINKS; ++g) {
+      if (lane == g) {
+        ax = (g & 1) ? k2[g >> 1].ax.y : k2[g >> 1].ax.x; ay = (g & 1) ? k2[g >> 1].ay.y : k2[g >> 1].ay.x;
+        az = (g & 1) ? k2[g >> 1].az.y : k2[g >> 1].az.x;
+      }
+    }
+    const int j = b * REM_SINKS + lane;
+    if (lane < REM_SINKS && j < it.sink_count) {
+      const int gi = it.sink_begin + j;
+      const float c = P.fcoeff * __ldg(&P.src4[gi].w);
+      P.vx[gi] = fmaf(c, ax, P.vx[gi]); P.vy[gi] = fmaf(c, ay, P.vy[gi]); P.vz[gi] = fmaf(c, az, P.vz[gi]);
+    }
+    if (COUNT) {
+#pragma unroll
+      for (int g = 0; g < REM_SINKS; ++g)
+        if (b * REM_SINKS + g < it.sink_count) { c64 += cnt[g]; f64 += nf[g]; }
+    }
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) { c64 += __shfl_down_sync(0xffffffffu, c64, o); f64 += __shfl_down_sync(0xffffffffu, f64, o); }
+    if (lane == 0) { atomicAdd(P.incut, c64); if (FUSED == 2) atomicAdd(P.incut + 1, f64); }
+  }
+}
+
 template <int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM, int FUSED>
 __device__ __forceinline__ void dispatch_item(int S, const WorkItem it, const ForceParams &P, float4 (*tiles)[FTILE],
                                               unsigned long long *bars) {
@@ -416,37 +537,82 @@ __global__ void __launch_bounds__(32) k_force(const __grid_constant__ ForceParam
     else run_item<0, SMAX_, NC, LAW, GUARD0, COUNT, false, false>(it, P, tiles, bars);
     return;
   }
-  if (P.unit_mass && it.no_pseudo) dispatch_item<NC, LAW, GUARD0, COUNT, true, FUSED>(S, it, P, tiles, bars);
+  if (P.unit_mass && (it.no_pseudo & 1)) dispatch_item<NC, LAW, GUARD0, COUNT, true, FUSED>(S, it, P, tiles, bars);
   else dispatch_item<NC, LAW, GUARD0, COUNT, false, FUSED>(S, it, P, tiles, bars);
 }
 
-// ---- work items: each sink leaf is cut into equal chunks of <= 32*SMAX_ sinks ---------------------------
+// the remainder items of the same item array (LAW 0 / 1 only: the packed pair arithmetic)
+template <int NC, int LAW, bool GUARD0, bool COUNT, int FUSED>
+__global__ void __launch_bounds__(32) k_force_rem(const __grid_constant__ ForceParams P, int n_items) {
+  __shared__ __align__(128) float4 tiles[REM_STAGES][FTILE];
+  __shared__ __align__(8) unsigned long long bars[REM_STAGES];
+  const int item = blockIdx.x;
+  if (item >= n_items) return;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < REM_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const WorkItem it = P.items[item];
+  if (P.unit_mass && (it.no_pseudo & 1)) run_item_rem<REM_STAGES, NC, LAW, GUARD0, COUNT, true, FUSED>(it, P, tiles, bars);
+  else run_item_rem<REM_STAGES, NC, LAW, GUARD0, COUNT, false, FUSED>(it, P, tiles, bars);
+}
+
+// ---- work items -------------------------------------------------------------------------------------------
+// The G = count / 32 full groups of a sink leaf are cut into ceil(G / SMAX_) chunks of nearly equal size; the
+// r = count mod 32 sinks left over become one remainder item (run_item_rem) when r <= REM_MAX and the law has a
+// packed form, else one more (padded) group.
+struct LeafCut { int groups, chunks, rem; };
+// policy 1: remainder items (default); 0: the r leftover sinks always become one more padded group
+__device__ __forceinline__ LeafCut leaf_cut(int count, int policy) {
+  LeafCut c;
+  c.groups = count / 32; c.rem = count % 32;
+  if (!(policy & 1) || c.rem > REM_MAX) { c.groups += c.rem ? 1 : 0; c.rem = 0; }
+  c.chunks = (c.groups + SMAX_ - 1) / SMAX_;
+  return c;
+}
+// groups of chunk q (0 <= q < chunks): balanced.  (Cutting by whole packed pairs -- even group counts, the odd group
+// runs the scalar form -- was measured and makes no difference: 94.1 vs 93.5 ms.)
+__device__ __forceinline__ int chunk_groups(const LeafCut &c, int q) {
+  return c.groups / c.chunks + (q < c.groups % c.chunks ? 1 : 0);
+}
 __global__ void k_item_count(const Node *__restrict__ nodes, const unsigned *__restrict__ n_ranges, int n_nodes,
-                             unsigned *__restrict__ item_cnt) {
+                             int policy, unsigned *__restrict__ item_cnt) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_nodes) return;
   unsigned c = 0;
-  if (n_ranges[k] > 0) c = (unsigned)((nodes[k].count + 32 * SMAX_ - 1) / (32 * SMAX_));
+  if (n_ranges[k] > 0) {
+    const LeafCut lc = leaf_cut(nodes[k].count, policy);
+    c = (unsigned)(lc.chunks + (lc.rem ? 1 : 0));
+  }
   item_cnt[k] = c;
 }
 __global__ void k_item_fill(const Node *__restrict__ nodes, const unsigned *__restrict__ item_cnt,
                             const unsigned *__restrict__ item_off, const unsigned *__restrict__ n_pseudo, int n_nodes,
-                            WorkItem *__restrict__ items) {
+                            int policy, WorkItem *__restrict__ items) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_nodes) return;
-  unsigned c = item_cnt[k];
-  if (c == 0) return;
-  int cnt = nodes[k].count, off = nodes[k].offset;
-  int per = (cnt + (int)c - 1) / (int)c;          // balanced chunks
-  per = (per + 31) & ~31;                          // whole 32-sink groups, except the last chunk
-  for (unsigned q = 0; q < c; ++q) {
+  if (item_cnt[k] == 0) return;
+  const int cnt = nodes[k].count, off = nodes[k].offset;
+  const LeafCut lc = leaf_cut(cnt, policy);
+  const int nopseudo = n_pseudo[k] == 0 ? 1 : 0;
+  unsigned o = item_off[k];
+  int g0 = 0;
+  for (int q = 0; q < lc.chunks; ++q) {
+    const int ng = chunk_groups(lc, q);
     WorkItem w;
-    w.node = k; w.sink_begin = off + (int)q * per;
-    int left = cnt - (int)q * per;
-    w.sink_count = left < per ? left : per;
-    if (w.sink_count < 0) w.sink_count = 0;
-    w.no_pseudo = n_pseudo[k] == 0 ? 1 : 0;
-    items[item_off[k] + q] = w;
+    w.node = k; w.sink_begin = off + 32 * g0;
+    const int left = cnt - 32 * g0 - lc.rem;           // the last group may be a padded one
+    w.sink_count = left < 32 * ng ? left : 32 * ng;
+    w.no_pseudo = nopseudo;
+    items[o++] = w;
+    g0 += ng;
+  }
+  if (lc.rem) {
+    WorkItem w;
+    w.node = k; w.sink_begin = off + 32 * lc.groups; w.sink_count = lc.rem; w.no_pseudo = nopseudo | ITEM_REM;
+    items[o++] = w;
   }
 }
 
@@ -461,12 +627,14 @@ static constexpr int MAX_GROUPS = 8;
 // haccsr_kick_host, which copies the velocities of a range to the host as soon as the launches up to that range have
 // finished, so only the last range's copy is exposed after the force kernel.  Inside each group the order is LPT.
 __device__ __forceinline__ int lpt_bin(const WorkItem &w, const unsigned *__restrict__ list_len, int groups, int n) {
-  float work = (float)((w.sink_count + 31) / 32) * (float)list_len[w.node];
+  const int rem = (w.no_pseudo & ITEM_REM) ? 1 : 0;
+  const float groups_eq = rem ? 0.25f * (float)((w.sink_count + REM_SINKS - 1) / REM_SINKS) : (float)((w.sink_count + 31) / 32);
+  float work = groups_eq * (float)list_len[w.node];
   int b = (int)(16.0f * __log2f(work + 1.0f));
   b = b < 0 ? 0 : (b > LPT_BINS - 1 ? LPT_BINS - 1 : b);
   int g = (int)(((long long)w.sink_begin * groups) / (n > 0 ? n : 1));
   g = g < 0 ? 0 : (g > groups - 1 ? groups - 1 : g);
-  return g * LPT_BINS + (LPT_BINS - 1 - b);       // heavy items first
+  return (2 * g + rem) * LPT_BINS + (LPT_BINS - 1 - b);       // segment (group, chunk | remainder items), heavy items first
 }
 __global__ void k_lpt_hist(const WorkItem *__restrict__ items, const unsigned *__restrict__ list_len, int n, int groups,
                            int n_part, unsigned *__restrict__ hist) {
@@ -483,16 +651,26 @@ __global__ void k_lpt_scatter(const WorkItem *__restrict__ items, const unsigned
 
 template <int NC, int LAW, bool GUARD0, int FUSED = 0>
 static int launch_force(haccsr_ctx *c, const ForceParams &P0, int n_items, bool count) {
-  // one launch per group of items (a single group unless haccsr_kick_host asked for range-wise velocity copies)
+  // per group of items (a single group unless haccsr_kick_host asked for range-wise velocity copies): one launch for the
+  // chunk items, one for the remainder items
   const int groups = c->force_groups;
   for (int g = 0; g < groups; ++g) {
-    const int b = groups > 1 ? (int)c->group_off[g] : 0, e = groups > 1 ? (int)c->group_off[g + 1] : n_items;
-    if (e > b) {
+    for (int rem = 0; rem < 2; ++rem) {
+      const int b = (int)c->seg_off[2 * g + rem], e = (int)c->seg_off[2 * g + rem + 1];
+      if (e <= b) continue;
       ForceParams P = P0;
       P.items = P0.items + b;
-      if (count) k_force<NC, LAW, GUARD0, true, FUSED><<<e - b, 32, 0, c->stream>>>(P, e - b);
-      else k_force<NC, LAW, GUARD0, false, FUSED><<<e - b, 32, 0, c->stream>>>(P, e - b);
-      c->launches++; c->force_launches++;
+      if (rem) {
+        if (LAW <= 1) {
+          if (count) k_force_rem<NC, (LAW <= 1 ? LAW : 0), GUARD0, true, FUSED><<<e - b, 32, 0, c->stream>>>(P, e - b);
+          else k_force_rem<NC, (LAW <= 1 ? LAW : 0), GUARD0, false, FUSED><<<e - b, 32, 0, c->stream>>>(P, e - b);
+        } else { set_error("remainder items for a law without a packed kernel"); return 1; }
+      } else {
+        if (count) k_force<NC, LAW, GUARD0, true, FUSED><<<e - b, 32, 0, c->stream>>>(P, e - b);
+        else k_force<NC, LAW, GUARD0, false, FUSED><<<e - b, 32, 0, c->stream>>>(P, e - b);
+      }
+      c->launches++;
+      if (!rem) c->force_launches++;     // haccsr_stats::force_launches counts the groups (k_force launches)
       HSR_CUDA(cudaGetLastError());
     }
     if (groups > 1 && c->ho_v[0]) {
@@ -512,7 +690,9 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   cudaStream_t s = c->stream;
   const int nn = c->n_nodes;
   HSR_TRY(c->item_cnt.ensure(nn + 1)); HSR_TRY(c->item_off.ensure(nn + 1));
-  k_item_count<<<(nn + 255) / 256, 256, 0, s>>>(c->nodes.p, c->n_ranges.p, nn, c->item_cnt.p);
+  // remainder items need a packed pair kernel: the polynomial and Newton laws
+  int use_rem = (c->law.kind == HACCSR_LAW_SR_POLY || c->law.kind == HACCSR_LAW_NEWTON) ? c->item_policy : 0;
+  k_item_count<<<(nn + 255) / 256, 256, 0, s>>>(c->nodes.p, c->n_ranges.p, nn, use_rem, c->item_cnt.p);
   c->launches++;
   HSR_TRY(scan_exclusive(c, c->item_cnt.p, c->item_off.p, nn, c->d_counters + 10));
   HSR_CUDA(cudaMemsetAsync(c->d_counters + 11, 0, 2 * sizeof(unsigned long long), s));   // in-cutoff pairs, force-law pairs
@@ -522,29 +702,26 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   if (c->n_items > 0x7fffffffll) { set_error("too many force work items"); return 1; }
   if (c->n_items == 0) return 0;
   HSR_TRY(c->items.ensure((size_t)c->n_items));
-  k_item_fill<<<(nn + 255) / 256, 256, 0, s>>>(c->nodes.p, c->item_cnt.p, c->item_off.p, c->n_pseudo.p, nn, c->items.p);
+  k_item_fill<<<(nn + 255) / 256, 256, 0, s>>>(c->nodes.p, c->item_cnt.p, c->item_off.p, c->n_pseudo.p, nn, use_rem, c->items.p);
   c->launches++;
   {
     const int ni = (int)c->n_items;
-    const int groups = c->force_groups, nb = groups * LPT_BINS, npart = (int)c->n_tree;
-    HSR_TRY(c->items_sorted.ensure((size_t)c->n_items)); HSR_TRY(c->lpt_hist.ensure(2 * (size_t)MAX_GROUPS * LPT_BINS));
-    unsigned *hist = c->lpt_hist.p, *cursor = c->lpt_hist.p + MAX_GROUPS * LPT_BINS;
+    const int groups = c->force_groups, nseg = 2 * groups, nb = nseg * LPT_BINS, npart = (int)c->n_tree;
+    HSR_TRY(c->items_sorted.ensure((size_t)c->n_items)); HSR_TRY(c->lpt_hist.ensure(4 * (size_t)MAX_GROUPS * LPT_BINS));
+    unsigned *hist = c->lpt_hist.p, *cursor = c->lpt_hist.p + 2 * MAX_GROUPS * LPT_BINS;
     HSR_CUDA(cudaMemsetAsync(hist, 0, nb * sizeof(unsigned), s));
     k_lpt_hist<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, groups, npart, hist);
     c->launches++;
     HSR_TRY(scan_exclusive(c, hist, cursor, nb, nullptr));
-    if (groups > 1) {   // first item of every group, for the launch configuration
-      HSR_CUDA(cudaMemcpy2DAsync(c->h_counters + 16, sizeof(int64_t), cursor, LPT_BINS * sizeof(unsigned), sizeof(unsigned),
-                                 groups, cudaMemcpyDeviceToHost, s));
-    }
+    // first item of every segment (group x {chunk items, remainder items}), for the launch configuration
+    HSR_CUDA(cudaMemcpy2DAsync(c->h_counters + 16, sizeof(int64_t), cursor, LPT_BINS * sizeof(unsigned), sizeof(unsigned),
+                               nseg, cudaMemcpyDeviceToHost, s));
     k_lpt_scatter<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, groups, npart, cursor, c->items_sorted.p);
     c->launches++;
     HSR_CUDA(cudaGetLastError());
-    if (groups > 1) {
-      HSR_CUDA(cudaStreamSynchronize(s));
-      for (int g = 0; g < groups; ++g) c->group_off[g] = (int64_t)(uint32_t)(c->h_counters[16 + g] & 0xffffffffll);
-      c->group_off[groups] = ni;
-    }
+    HSR_CUDA(cudaStreamSynchronize(s));
+    for (int g = 0; g < nseg; ++g) c->seg_off[g] = (int64_t)(uint32_t)(c->h_counters[16 + g] & 0xffffffffll);
+    c->seg_off[nseg] = ni;
   }
 
   ForceParams P;
