@@ -38,7 +38,8 @@ class KickOpts(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "csrc", "libhaccsr.so")
+    # HACCSR_LIB: another build of the same library (tuning experiments); the default is the in-tree build
+    return os.environ.get("HACCSR_LIB") or os.path.join(_HERE, "csrc", "libhaccsr.so")
 
 
 _LIB = None

@@ -322,6 +322,40 @@ def test_ragged_sizes(oracle, n, arith):
         assert np.median(rel) < 5e-6
 
 
+@pytest.mark.parametrize("arith", ARITHS)
+@pytest.mark.parametrize("tdpts", [1, 12])
+def test_remainder_items_match_padded_groups(oracle, arith, tdpts, monkeypatch):
+    """The count mod 32 leftover sinks of a leaf run as remainder items (sources over lanes, k_force_rem) by default and as
+    one more padded group with HACCSR_ITEM_POLICY=0: same pair counts (exact), same kicks to FP32 rounding (the 32-way
+    interleaved sum of a remainder sink against the sequential one), every other sink bit-identical; both against the
+    oracle.  Leaf sizes are ragged (clustered snapshot, ppn 100), so remainders 1..31 and multi-batch items all occur."""
+    p = synth.clustered(30000, 24.0, seed=41)
+    b = boxes(24)
+    theta = 0.3 if tdpts == 12 else 0.5
+    monkeypatch.setenv("HACCSR_ITEM_POLICY", "0")
+    pad, st0, tr0, _ = gpu_run(p, b, theta, 100, arith=arith, tdpts=tdpts)
+    monkeypatch.setenv("HACCSR_ITEM_POLICY", "1")
+    rem, st1, tr1, _ = gpu_run(p, b, theta, 100, arith=arith, tdpts=tdpts)
+    assert st1["pairs_evaluated"] == st0["pairs_evaluated"] and st1["pairs_in_cutoff"] == st0["pairs_in_cutoff"]
+    assert np.array_equal(pad["id"], rem["id"])
+    # which sinks are remainder sinks: the last count % 32 (<= 24) particles of every sink leaf
+    isrem = np.zeros(p["x"].size, bool)
+    leaf = (tr1["cl"] == 0) & (tr1["cr"] == 0) & (tr1["count"] > 0)
+    for off, cnt in zip(tr1["offset"][leaf], tr1["count"][leaf]):
+        r = cnt % 32
+        if 0 < r <= 24:
+            isrem[off + cnt - r:off + cnt] = True
+    assert isrem.sum() > 1000
+    for k in ("vx", "vy", "vz"):
+        assert np.array_equal(pad[k][~isrem], rem[k][~isrem]), k
+    og = oracle.run(p, *b, RSM, theta, 100, form=oracle.FORM_GROSS, tdpts=tdpts)
+    gross = np.maximum(by_id(og)["vx"].astype(np.float64), 1e-30)
+    d = _dist(by_id(pad), by_id(rem))
+    assert (d / (gross + 1e-3)).max() <= 1e-5
+    moved = isrem[np.argsort(rem["id"])] & (d > 0)
+    assert moved.sum() > 0.1 * isrem.sum()              # the remainder path really ran (different summation order)
+
+
 def test_coincident_particles_and_oversized_leaf(oracle):
     n = 700     # > 32*8 sinks: the leaf is cut into several sink chunks
     p = synth._pack(np.full(n, 3.0), np.full(n, 4.0), np.full(n, 5.0))
@@ -579,6 +613,36 @@ def test_full_size_properties():
         assert abs(v.sum()) < 1e-6 * np.abs(v).sum()
     assert 7000 < st["pairs_evaluated"] / n < 12000
     del torch
+
+
+def test_c1_full_size_against_compiled_reference():
+    """BASELINE configs[0] in full: np = ng = 128 alive + the 11-cell overload shell (150^3 grid units, 3.4 M particles),
+    z = 50 Zel'dovich snapshot from the shipped transfer function, ppn 512, theta 0.5, poly5 -- the GPU kick against the
+    COMPILED reference constructor (oracle/_ref, ~30 s on 16 host cores) on the identical snapshot: same tree census, same
+    number of evaluated pairs (counted by the reference's own nbody1 through a counting ForceLaw), every particle's kick
+    within 1e-4 of the rms kick and 5e-6 in the median (FP32, documented summation order)."""
+    from oracle import refbind
+    if not refbind.available():
+        pytest.skip("oracle/_ref/libhaccref.so not built (needs /root/reference at build time)")
+    p = synth.zeldovich_torch(128, z=50.0, seed=5009888, ghost=11, device="cuda")
+    side = 150.0
+    b = ([0.0] * 3, [side] * 3, [3.2] * 3, [side - 3.2] * 3)
+    ref, rst, _ = refbind.rcb_kick(p, *b, RSM, THETA, 512, fcoeff=1.0, law=refbind.LAW_POLY5, count_pairs=True)
+    for arith in (H.ARITH_FUSED, H.ARITH_X86):
+        out, st, _, _ = gpu_run(p, b, THETA, 512, want_tree=False, arith=arith)
+        assert st["nodes"] == rst["nodes"] and st["leaves"] == rst["leaves"] and st["max_ppn"] == rst["max_ppn"]
+        assert st["pairs_evaluated"] == rst["pairs_eval"]
+        if arith == H.ARITH_X86:
+            assert st["pairs_in_cutoff"] == rst["pairs_incut"]          # the x86 build's in-cutoff pair set, bit for bit
+        else:
+            assert abs(st["pairs_in_cutoff"] - rst["pairs_incut"]) <= 1e-6 * rst["pairs_incut"]
+        keys = ("vx", "vy", "vz", "x", "mass")
+        a, r = by_id(out, keys), by_id(ref, keys)
+        d = _dist(a, r)
+        rms = np.sqrt(np.mean(sum(r[k].astype(np.float64) ** 2 for k in ("vx", "vy", "vz"))))
+        assert np.median(d) <= 5e-6 * rms and np.quantile(d, 0.999) <= 3e-5 * rms and d.max() <= 1e-4 * rms, (
+            arith, np.median(d) / rms, np.quantile(d, 0.999) / rms, d.max() / rms)
+        assert np.array_equal(a["x"], r["x"]) and np.array_equal(a["mass"], r["mass"])
 
 
 @pytest.mark.parametrize("law,theta,quad", [("poly", 0.5, False), ("fit", 0.1, False), ("interp", 0.5, False), ("newton", 0.5, False),

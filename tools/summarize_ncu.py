@@ -28,7 +28,11 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us"
 
 
 def load(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if path.endswith(".csv"):       # already exported on the GPU box: ncu -i X.ncu-rep --page raw --csv > X_raw.csv
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    out = "\n".join(l for l in out.splitlines() if l.startswith('"'))
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 
@@ -53,14 +57,14 @@ def main():
         i = col.get(m)
         if i is None:
             return None
-        vals = [float(r[i].replace(",", "")) for r in rs if r[i] not in ("", "n/a")]
+        vals = [float(r[i].replace(",", "")) for r in rs if r[i] not in ("", "n/a", "nan")]
         if not vals:
             return None
         return sum(vals) / len(vals) * SCALE.get(units[i], 1.0)
 
     if a.traffic:
         for k, rs in groups.items():
-            if k.startswith(a.traffic):
+            if k == a.traffic or k.startswith(a.traffic + "<"):
                 print(int(mean(rs, "dram__bytes_read.sum") + mean(rs, "dram__bytes_write.sum")))
         return
     names = list(groups)
