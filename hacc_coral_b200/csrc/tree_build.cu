@@ -184,19 +184,9 @@ __device__ __forceinline__ void flush_part(const Part &p, int nd, int n0, Slot *
 // block and fell back to per-thread shared atomics; the second combined per-thread partials of 4 consecutive
 // particles with a 14-word segmented warp scan -- 75 shuffles per 128 particles, issue-bound at 35 % of the HBM peak,
 // profiles/r1j_build_ncu_summary.md.)
-#ifndef HSR_CM_IPT
-#define HSR_CM_IPT 8
-#endif
-#ifndef HSR_CM_MINB
-#define HSR_CM_MINB 1
-#endif
-#ifndef HSR_LC_MINB
-#define HSR_LC_MINB 1
-#endif
-#ifndef HSR_SC_MINB
-#define HSR_SC_MINB 1
-#endif
-static constexpr int CM_IPT = HSR_CM_IPT;
+// (8 rows, no register cap: 4 rows or __launch_bounds__ minimum-block counts of 3-4 on any of the three tile kernels
+// spill and were 4-18 % slower on the whole build)
+static constexpr int CM_IPT = 8;
 static constexpr int CM_TILE = TPB * CM_IPT;
 
 __device__ __forceinline__ long long shfl_xor_ll(long long v, int o) {
@@ -205,7 +195,7 @@ __device__ __forceinline__ long long shfl_xor_ll(long long v, int o) {
   return ((long long)hi << 32) | (long long)(unsigned)lo;
 }
 
-__global__ void __launch_bounds__(TPB, HSR_CM_MINB) k_cm_tile(const float4 *__restrict__ rec, const int *__restrict__ nid, int n,
+__global__ void __launch_bounds__(TPB) k_cm_tile(const float4 *__restrict__ rec, const int *__restrict__ nid, int n,
                                                  NodeAcc *__restrict__ acc, const float *__restrict__ scales) {
   __shared__ int s_n0;
   __shared__ Slot slots[SMAX];
@@ -396,7 +386,7 @@ __device__ __forceinline__ int tile_flags_scan(const Node *__restrict__ nodes, c
   return s_w[32];
 }
 
-__global__ void __launch_bounds__(TPB, HSR_LC_MINB) k_left_count(const float4 *__restrict__ rec, const int *__restrict__ nid,
+__global__ void __launch_bounds__(TPB) k_left_count(const float4 *__restrict__ rec, const int *__restrict__ nid,
                                                     const Node *__restrict__ nodes, int n, int ntiles,
                                                     unsigned *__restrict__ tilecount, int *__restrict__ lstart,
                                                     int *__restrict__ lend) {
@@ -466,7 +456,7 @@ __global__ void k_set_children(Node *__restrict__ nodes, int begin, int end, con
   nodes[nd.cr].count = nd.count - is; nodes[nd.cr].offset = nd.offset + is;    // :732,762
 }
 
-__global__ void __launch_bounds__(TPB, HSR_SC_MINB) k_scatter(const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
+__global__ void __launch_bounds__(TPB) k_scatter(const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
                                                  const int *__restrict__ nid, const Node *__restrict__ nodes, int n,
                                                  int ntiles, const unsigned *__restrict__ tilebase,
                                                  const int *__restrict__ lbase, const int *__restrict__ nleft,
