@@ -137,7 +137,7 @@ int haccsr_create(haccsr_ctx **out, int device, int64_t max_particles) {
   haccsr_ctx *c = new (std::nothrow) haccsr_ctx();
   if (!c) { set_error("out of host memory"); return 2; }
   c->device = device; c->sm_count = prop.multiProcessorCount; c->cap = max_particles;
-  if (const char *e = getenv("HACCSR_ITEM_POLICY")) c->item_policy = atoi(e) & 1;
+  if (const char *e = getenv("HACCSR_ITEM_POLICY")) c->item_policy = atoi(e) & 0x71;   // bit 0: remainder items; bits 4-6: largest chunk in groups (tuning)
   int rc = 0;
   do {
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = 2; break; }

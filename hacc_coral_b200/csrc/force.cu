@@ -569,7 +569,8 @@ __device__ __forceinline__ LeafCut leaf_cut(int count, int policy) {
   LeafCut c;
   c.groups = count / 32; c.rem = count % 32;
   if (!(policy & 1) || c.rem > REM_MAX) { c.groups += c.rem ? 1 : 0; c.rem = 0; }
-  c.chunks = (c.groups + SMAX_ - 1) / SMAX_;
+  const int maxg = (policy >> 4) ? (policy >> 4) : SMAX_;      // tuning: largest chunk in groups (<= SMAX_)
+  c.chunks = (c.groups + maxg - 1) / maxg;
   return c;
 }
 // groups of chunk q (0 <= q < chunks): balanced.  (Cutting by whole packed pairs -- even group counts, the odd group
