@@ -52,7 +52,7 @@ static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
 // Build-time accumulators of a node: order-independent (integer) so the build is deterministic.
 struct NodeAcc {
   unsigned umin[3], umax[3];         // order-preserving uint encoding of float min / max
-  unsigned long long lo[4], hi[4];   // 128-bit fixed-point sums of w*x, w*y, w*z, w
+  unsigned long long lo[4], hi[4];   // exact fixed-point sums of w*x, w*y, w*z, w: total = hi * 2^32 + lo (tree_build.cu add_split)
 };
 
 struct ForceLawParams {

@@ -43,19 +43,22 @@ __device__ __forceinline__ unsigned enc_f(float f) {   // order-preserving float
 __device__ __forceinline__ float dec_f(unsigned u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
-__device__ __forceinline__ void add128(unsigned long long *lo, unsigned long long *hi, long long v) {
+// Exact sums wider than 64 bits without a carry chain: a contribution v (a per-block int64 sum) is split as
+// v = (v >> 32) * 2^32 + (v & 0xffffffff) and the two parts are added to two 64-bit words with result-less atomics (RED):
+// the block does not wait for the returned value that a lo/hi carry would need.  total = hi * 2^32 + lo (hi signed).
+// Headroom: |v| < 2^62 per block, so hi grows by < 2^30 and lo by < 2^32 per block: exact for > 2^31 blocks.
+__device__ __forceinline__ void add_split(unsigned long long *lo, unsigned long long *hi, long long v) {
   if (v == 0) return;
-  unsigned long long uv = (unsigned long long)v;
-  unsigned long long old = atomicAdd(lo, uv);
-  unsigned long long carry = (old + uv < old) ? 1ull : 0ull;
-  unsigned long long h = carry + (v < 0 ? ~0ull : 0ull);
-  if (h) atomicAdd(hi, h);
+  atomicAdd(lo, (unsigned long long)(v & 0xffffffffll));
+  atomicAdd(hi, (unsigned long long)(v >> 32));
 }
-__device__ __forceinline__ double to_double128(unsigned long long lo, unsigned long long hi) {
-  // two's-complement 128-bit -> double via the magnitude (avoids cancellation for small negative sums)
-  bool neg = (hi >> 63) != 0;
-  if (neg) { lo = ~lo + 1ull; hi = ~hi + (lo == 0 ? 1ull : 0ull); }
-  double d = (double)hi * 18446744073709551616.0 + (double)lo;
+__device__ __forceinline__ double split_to_double(unsigned long long lo, unsigned long long hi) {
+  // hi * 2^32 + lo as a 128-bit two's-complement integer, then -> double via the magnitude (avoids cancellation for
+  // small negative sums)
+  const __int128 t = ((__int128)(long long)hi << 32) + (__int128)lo;
+  const bool neg = t < 0;
+  const unsigned __int128 m = neg ? (unsigned __int128)(-t) : (unsigned __int128)t;
+  const double d = (double)(unsigned long long)(m >> 64) * 18446744073709551616.0 + (double)(unsigned long long)m;
   return neg ? -d : d;
 }
 __device__ __forceinline__ float comp(const float4 &r, int d) { return d == 0 ? r.x : (d == 1 ? r.y : r.z); }
@@ -172,7 +175,7 @@ __device__ __forceinline__ void flush_part(const Part &p, int nd, int n0, Slot *
   } else {
     NodeAcc &A = acc[nd];
     for (int k = 0; k < 3; ++k) { atomicMin(&A.umin[k], p.umin[k]); atomicMax(&A.umax[k], p.umax[k]); }
-    for (int k = 0; k < 4; ++k) add128(&A.lo[k], &A.hi[k], p.s[k]);
+    for (int k = 0; k < 4; ++k) add_split(&A.lo[k], &A.hi[k], p.s[k]);
   }
 }
 
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(TPB) k_cm_tile(const float4 *__restrict__ rec,
     NodeAcc &A = acc[n0 + t];
     const Slot &S = slots[t];
     for (int k = 0; k < 3; ++k) { atomicMin(&A.umin[k], S.umin[k]); atomicMax(&A.umax[k], S.umax[k]); }
-    for (int k = 0; k < 4; ++k) add128(&A.lo[k], &A.hi[k], (long long)S.s[k]);
+    for (int k = 0; k < 4; ++k) add_split(&A.lo[k], &A.hi[k], (long long)S.s[k]);
   }
 }
 
@@ -270,9 +273,9 @@ __global__ void __launch_bounds__(256) k_level_decide(Node *__restrict__ nodes, 
   if (nd.count > 0) {
     const NodeAcc a = acc[k];
     for (int q = 0; q < 3; ++q) { nd.xmin[q] = dec_f(a.umin[q]); nd.xmax[q] = dec_f(a.umax[q]); }
-    const double sw = to_double128(a.lo[3], a.hi[3]);
+    const double sw = split_to_double(a.lo[3], a.hi[3]);
     for (int q = 0; q < 3; ++q) {
-      const double sxq = to_double128(a.lo[q], a.hi[q]);
+      const double sxq = split_to_double(a.lo[q], a.hi[q]);
       nd.xc[q] = (float)((sxq / sw) * undo);                       // BGQCM.c:209-211
     }
     if (nd.count > ppn) {                                          // RCBForceTree.cxx:788
@@ -417,17 +420,25 @@ __global__ void __launch_bounds__(TPB) k_left_count(const float4 *__restrict__ r
   }
 }
 
-// single-block exclusive scan (n up to a few million; used on per-tile and per-node counts)
+// single-block exclusive scan (per-tile and per-node counts: up to a few hundred thousand values); 8 consecutive values
+// per thread and iteration, so 21 k tile counts take 3 rounds of the block scan instead of 21
 __global__ void __launch_bounds__(1024) k_scan(const unsigned *__restrict__ in, unsigned *__restrict__ out,
                                                long long n, unsigned long long *__restrict__ d_total) {
   __shared__ int s_w[34];
+  constexpr int PER = 8;
   unsigned long long running = 0;
-  for (long long b = 0; b < n; b += blockDim.x) {
-    long long i = b + threadIdx.x;
-    int v = (i < n) ? (int)in[i] : 0;
+  for (long long b = 0; b < n; b += (long long)blockDim.x * PER) {
+    const long long i0 = b + (long long)threadIdx.x * PER;
+    unsigned v[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) v[j] = (i0 + j < n) ? in[i0 + j] : 0u;
+    unsigned t = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { const unsigned x = v[j]; v[j] = t; t += x; }
     int total;
-    int e = block_excl_scan(v, s_w, &total);
-    if (i < n) out[i] = (unsigned)(running + (unsigned long long)e);
+    const unsigned long long base = running + (unsigned long long)(unsigned)block_excl_scan((int)t, s_w, &total);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) if (i0 + j < n) out[i0 + j] = (unsigned)(base + v[j]);
     running += (unsigned long long)(unsigned)total;
   }
   if (threadIdx.x == 0 && d_total) *d_total = running;
