@@ -409,7 +409,8 @@ __device__ __noinline__ void produce_tile_rep(ProducerRep &q, const ForceParams 
 
 template <int NST, int NC, int LAW, bool GUARD0, bool COUNT, bool UNITM, int FUSED>
 __device__ __forceinline__ void run_item_rem(const WorkItem it, const ForceParams &P, float4 (*tiles)[FTILE],
-                                             unsigned long long *bars) {
+                                             unsigned long long *bars, volatile float2 *sink_sm_v) {
+  float2 *sink_sm = const_cast<float2 *>(sink_sm_v);
   constexpr int S2 = REM_SINKS / 2;
   const int lane = threadIdx.x;
   const unsigned total = P.list_len[it.node];
@@ -426,14 +427,21 @@ __device__ __forceinline__ void run_item_rem(const WorkItem it, const ForceParam
   unsigned long long c64 = 0, f64 = 0;
   for (int b = 0; b < nbatch; ++b) {
     SinkRegs2 k2[S2];
-#pragma unroll
-    for (int g = 0; g < REM_SINKS; ++g) {
-      const int j = b * REM_SINKS + g;   // sinks past the end re-use the item's first sink (result discarded)
+    // the batch's sinks go through shared memory in packed layout and come back as 64-bit loads, i.e. in aligned register
+    // pairs: left to itself ptxas keeps the float4 loads and re-packs every operand pair with two MOVs inside the pair
+    // loop (24 of 123 instructions per iteration)
+    __syncwarp();
+    if (lane < REM_SINKS) {
+      const int j = b * REM_SINKS + lane;   // sinks past the end re-use the item's first sink (result discarded)
       const float4 s = __ldg(P.src4 + it.sink_begin + (j < it.sink_count ? j : 0));
-      SinkRegs2 &k = k2[g >> 1];
-      if ((g & 1) == 0) { k.nx.x = -s.x; k.ny.x = -s.y; k.nz.x = -s.z; }
-      else { k.nx.y = -s.x; k.ny.y = -s.y; k.nz.y = -s.z; }
+      float *f = reinterpret_cast<float *>(sink_sm);
+      f[(0 * S2 + (lane >> 1)) * 2 + (lane & 1)] = -s.x;
+      f[(1 * S2 + (lane >> 1)) * 2 + (lane & 1)] = -s.y;
+      f[(2 * S2 + (lane >> 1)) * 2 + (lane & 1)] = -s.z;
     }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < S2; ++k) { k2[k].nx = sink_sm[0 * S2 + k]; k2[k].ny = sink_sm[1 * S2 + k]; k2[k].nz = sink_sm[2 * S2 + k]; }
 #pragma unroll
     for (int k = 0; k < S2; ++k) k2[k].ax = k2[k].ay = k2[k].az = make_float2(0.f, 0.f);
     unsigned cnt[REM_SINKS], nf[REM_SINKS];
@@ -546,6 +554,7 @@ template <int NC, int LAW, bool GUARD0, bool COUNT, int FUSED>
 __global__ void __launch_bounds__(32) k_force_rem(const __grid_constant__ ForceParams P, int n_items) {
   __shared__ __align__(128) float4 tiles[REM_STAGES][FTILE];
   __shared__ __align__(8) unsigned long long bars[REM_STAGES];
+  __shared__ __align__(16) float2 sink_sm[3 * REM_SINKS / 2];
   const int item = blockIdx.x;
   if (item >= n_items) return;
   if (threadIdx.x == 0) {
@@ -555,8 +564,8 @@ __global__ void __launch_bounds__(32) k_force_rem(const __grid_constant__ ForceP
   }
   __syncwarp();
   const WorkItem it = P.items[item];
-  if (P.unit_mass && (it.no_pseudo & 1)) run_item_rem<REM_STAGES, NC, LAW, GUARD0, COUNT, true, FUSED>(it, P, tiles, bars);
-  else run_item_rem<REM_STAGES, NC, LAW, GUARD0, COUNT, false, FUSED>(it, P, tiles, bars);
+  if (P.unit_mass && (it.no_pseudo & 1)) run_item_rem<REM_STAGES, NC, LAW, GUARD0, COUNT, true, FUSED>(it, P, tiles, bars, sink_sm);
+  else run_item_rem<REM_STAGES, NC, LAW, GUARD0, COUNT, false, FUSED>(it, P, tiles, bars, sink_sm);
 }
 
 // ---- work items -------------------------------------------------------------------------------------------
