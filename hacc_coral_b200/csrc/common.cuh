@@ -172,6 +172,9 @@ struct haccsr_ctx {
   const void *pending_ho = nullptr;   // host output arrays whose device->host copies are not queued yet (api.cu)
   int64_t pending_count = 0;
   int force_groups = 1;
+  int64_t group_lo[9] = {0};          // particle ranges of the groups: [group_lo[g], group_lo[g+1])
+  int host_groups = 2;                // haccsr_kick_host: launches by particle range; the last one covers host_last_frac of the particles
+  float host_last_frac = 0.10f;       //   (0 = equal ranges).  Env HACCSR_HOST_GROUPS / HACCSR_HOST_LAST, for A/B measurements
   int64_t seg_off[17] = {0};          // item ranges of the launches: (group g, chunk items) = [2g, 2g+1), remainder items [2g+1, 2g+2)
   float *ho_v[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -633,30 +633,32 @@ __global__ void k_item_fill(const Node *__restrict__ nodes, const unsigned *__re
 // has no effect on results: every item owns its sinks.
 static constexpr int LPT_BINS = 512;
 static constexpr int MAX_GROUPS = 8;
-// Items can additionally be split into `groups` launches by particle range (group = sink_begin * groups / n): used by
+// Items can additionally be split into `groups` launches by particle range (haccsr_ctx::group_lo): used by
 // haccsr_kick_host, which copies the velocities of a range to the host as soon as the launches up to that range have
 // finished, so only the last range's copy is exposed after the force kernel.  Inside each group the order is LPT.
-__device__ __forceinline__ int lpt_bin(const WorkItem &w, const unsigned *__restrict__ list_len, int groups, int n) {
+struct GroupBounds { int groups; int lo[MAX_GROUPS + 1]; };
+__device__ __forceinline__ int lpt_bin(const WorkItem &w, const unsigned *__restrict__ list_len, const GroupBounds &G) {
   const int rem = (w.no_pseudo & ITEM_REM) ? 1 : 0;
   const float groups_eq = rem ? 0.25f * (float)((w.sink_count + REM_SINKS - 1) / REM_SINKS) : (float)((w.sink_count + 31) / 32);
   float work = groups_eq * (float)list_len[w.node];
   int b = (int)(16.0f * __log2f(work + 1.0f));
   b = b < 0 ? 0 : (b > LPT_BINS - 1 ? LPT_BINS - 1 : b);
-  int g = (int)(((long long)w.sink_begin * groups) / (n > 0 ? n : 1));
-  g = g < 0 ? 0 : (g > groups - 1 ? groups - 1 : g);
+  int g = 0;
+#pragma unroll
+  for (int q = 1; q < MAX_GROUPS; ++q) g += (q < G.groups && w.sink_begin >= G.lo[q]) ? 1 : 0;
   return (2 * g + rem) * LPT_BINS + (LPT_BINS - 1 - b);       // segment (group, chunk | remainder items), heavy items first
 }
-__global__ void k_lpt_hist(const WorkItem *__restrict__ items, const unsigned *__restrict__ list_len, int n, int groups,
-                           int n_part, unsigned *__restrict__ hist) {
+__global__ void k_lpt_hist(const WorkItem *__restrict__ items, const unsigned *__restrict__ list_len, int n,
+                           const GroupBounds G, unsigned *__restrict__ hist) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(&hist[lpt_bin(items[i], list_len, groups, n_part)], 1u);
+  if (i < n) atomicAdd(&hist[lpt_bin(items[i], list_len, G)], 1u);
 }
-__global__ void k_lpt_scatter(const WorkItem *__restrict__ items, const unsigned *__restrict__ list_len, int n, int groups,
-                              int n_part, unsigned *__restrict__ cursor, WorkItem *__restrict__ out) {
+__global__ void k_lpt_scatter(const WorkItem *__restrict__ items, const unsigned *__restrict__ list_len, int n,
+                              const GroupBounds G, unsigned *__restrict__ cursor, WorkItem *__restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   WorkItem w = items[i];
-  out[atomicAdd(&cursor[lpt_bin(w, list_len, groups, n_part)], 1u)] = w;
+  out[atomicAdd(&cursor[lpt_bin(w, list_len, G)], 1u)] = w;
 }
 
 template <int NC, int LAW, bool GUARD0, int FUSED = 0>
@@ -685,7 +687,7 @@ static int launch_force(haccsr_ctx *c, const ForceParams &P0, int n_items, bool 
     }
     if (groups > 1 && c->ho_v[0]) {
       // velocities of particles [lo, hi) are final once every launch up to this one is done
-      const int64_t n = c->n_tree, lo = n * g / groups, hi = n * (g + 1) / groups;
+      const int64_t lo = c->group_lo[g], hi = c->group_lo[g + 1];
       HSR_CUDA(cudaEventRecord(c->ev_grp[g], c->stream));
       HSR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_grp[g], 0));
       float *dv[3] = {c->cur.vx, c->cur.vy, c->cur.vz};
@@ -716,17 +718,20 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   c->launches++;
   {
     const int ni = (int)c->n_items;
-    const int groups = c->force_groups, nseg = 2 * groups, nb = nseg * LPT_BINS, npart = (int)c->n_tree;
+    const int groups = c->force_groups, nseg = 2 * groups, nb = nseg * LPT_BINS;
+    GroupBounds G;
+    G.groups = groups;
+    for (int g = 0; g <= MAX_GROUPS; ++g) G.lo[g] = (int)(g <= groups ? (groups > 1 ? c->group_lo[g] : (g ? c->n_tree : 0)) : c->n_tree);
     HSR_TRY(c->items_sorted.ensure((size_t)c->n_items)); HSR_TRY(c->lpt_hist.ensure(4 * (size_t)MAX_GROUPS * LPT_BINS));
     unsigned *hist = c->lpt_hist.p, *cursor = c->lpt_hist.p + 2 * MAX_GROUPS * LPT_BINS;
     HSR_CUDA(cudaMemsetAsync(hist, 0, nb * sizeof(unsigned), s));
-    k_lpt_hist<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, groups, npart, hist);
+    k_lpt_hist<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, G, hist);
     c->launches++;
     HSR_TRY(scan_exclusive(c, hist, cursor, nb, nullptr));
     // first item of every segment (group x {chunk items, remainder items}), for the launch configuration
     HSR_CUDA(cudaMemcpy2DAsync(c->h_counters + 16, sizeof(int64_t), cursor, LPT_BINS * sizeof(unsigned), sizeof(unsigned),
                                nseg, cudaMemcpyDeviceToHost, s));
-    k_lpt_scatter<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, groups, npart, cursor, c->items_sorted.p);
+    k_lpt_scatter<<<(ni + 255) / 256, 256, 0, s>>>(c->items.p, c->list_len.p, ni, G, cursor, c->items_sorted.p);
     c->launches++;
     HSR_CUDA(cudaGetLastError());
     HSR_CUDA(cudaStreamSynchronize(s));

@@ -508,7 +508,7 @@ def test_kick_host_equals_upload_kick_download():
 
 
 def test_kick_host_grouped_force_launches_bitwise():
-    """Above 2^20 particles haccsr_kick_host runs the force kernel as four launches by particle range and copies each
+    """Above 2^20 particles haccsr_kick_host runs the force kernel as several launches by particle range and copies each
     range's velocities out while the next one is computed: same bits as upload + kick + download."""
     p = synth.zeldovich(104, z=50.0, seed=33, ghost=0)       # 1.12 M particles
     rng = np.random.default_rng(2)
@@ -521,7 +521,7 @@ def test_kick_host_grouped_force_launches_bitwise():
     q = {k: np.ascontiguousarray(v).copy() for k, v in p.items()}
     s1 = g.kick_host(q, *b, 0.5, 256, fcoeff=0.5)
     g.close()
-    assert s1["force_launches"] == 4 and st["force_launches"] == 1
+    assert s1["force_launches"] >= 2 and st["force_launches"] == 1
     assert s1["pairs_evaluated"] == st["pairs_evaluated"]
     for k in ref:
         assert np.array_equal(q[k], ref[k]), k
