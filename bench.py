@@ -391,7 +391,7 @@ def main():
         line["roofline"]["executed_flop_per_interaction"] = ex
         line["roofline"]["frac_executed"] = line["roofline"]["frac"] * ex / FLOP_PER_PAIR
         line["config"]["culling"] = "on"
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the contract: rank 0 at N = 1 only (the reference arm covers every N)
         try:
             info = run_reference_sample(p, nglt, args)
         except Exception as ex:   # the baseline is a reported companion number; never fail the GPU line
