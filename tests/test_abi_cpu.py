@@ -72,3 +72,40 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cxx", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oraclebind" not in txt and "refbind" not in txt and "liboracle" not in txt, f
+
+
+def test_integration_level2_snippet_compiles(tmp_path):
+    """The reference-side change shown in INTEGRATION.md (Level 2: Particles::subCycle on the device) is compiled against
+    include/haccsr.h and the facade's ForceLaw.h with stand-ins for the reference's Particles / TimeStepper / Domain
+    members it touches (src/cpu/Particles.h:160-205, src/simulation/TimeStepper.h, Domain.h) -- the document cannot rot
+    against the C ABI."""
+    import subprocess
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```cpp\n(.*?)```", doc, flags=re.S)
+    snippet = [b for b in blocks if "void Particles::subCycle" in b]
+    assert len(snippet) == 1
+    stub = r'''
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <stdint.h>
+#include "ForceLaw.h"
+struct TimeStepper { float pp() const; float adot() const; float fscal() const; float tau() const; float tau2() const; };
+struct Domain { static void ng_local_total(int *); };
+static int local_gpu = 0;
+class Particles {
+ public:
+  void subCycle(TimeStepper *gts);
+ private:
+  float *m_xArr, *m_yArr, *m_zArr, *m_vxArr, *m_vyArr, *m_vzArr, *m_massArr, *m_phiArr;
+  int64_t *m_idArr; uint16_t *m_maskArr;
+  int64_t m_Np_local_total; int m_nsub, m_rcbTreePPN;
+  float m_edge, m_alpha, m_gpscal, m_openAngle, m_fsrrmax;
+  ForceLaw *m_fl;
+};
+'''
+    src = tmp_path / "level2.cxx"
+    src.write_text(stub + snippet[0])
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ROOT, "hacc_coral_b200", "host"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
