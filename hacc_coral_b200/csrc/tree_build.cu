@@ -16,7 +16,7 @@
 //   B2 k_set_children   per node: is = L(end) - L(begin); child counts / offsets; degenerate splits
 //   C3 k_scatter        stable two-way partition of (x,y,z,m | index) records into the other buffer;
 //                       particles of finished leaves are written once to the final tree-order arrays.
-// The centroid sums are accumulated as 128-bit fixed-point integers, so they are exact and independent
+// The centroid sums are accumulated as wide fixed-point integers (two 64-bit words, add_split), so they are exact and independent
 // of summation order: the build is deterministic, and the float centroid equals the reference's
 // (double-accumulated) one except where the reference's own rounding error straddles a float boundary.
 // Children are numbered breadth-first (parent index < child index, as the reference guarantees at :808-809).
