@@ -27,6 +27,8 @@
 #include <float.h>
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace haccsr {
 
@@ -255,6 +257,71 @@ __global__ void __launch_bounds__(TPB) k_cm_tile(const float4 *__restrict__ rec,
     for (int k = 0; k < 3; ++k) { atomicMin(&A.umin[k], S.umin[k]); atomicMax(&A.umax[k], S.umax[k]); }
     for (int k = 0; k < 4; ++k) add_split(&A.lo[k], &A.hi[k], (long long)S.s[k]);
   }
+}
+
+// Alternative k_cm_tile, selected with HACCSR_CM_KERNEL=warp (off by default: measured stand-alone only, see
+// tools/microbench_cm.cu and profiles/r1o_microbench_cm.txt -- identical accumulators, 6-25 % faster -- but the parity suite
+// has not been run on it inside the library yet).  Persistent warps over CONTIGUOUS particle ranges: the next rows' loads are
+// in flight during the current rows' arithmetic, the node's per-lane partial stays in registers while the node id stays the
+// same and is reduced and flushed with result-less global atomics only when the id changes; no shared memory, no barriers.
+static constexpr int CMW_ROWS = 4;
+__global__ void __launch_bounds__(TPB) k_cm_warp(const float4 *__restrict__ rec, const int *__restrict__ nid, int n,
+                                                 int per_warp, NodeAcc *__restrict__ acc, const float *__restrict__ scales) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long b64 = gw * (long long)per_warp;
+  if (b64 >= n) return;
+  const int begin = (int)b64, end = (int)min((long long)n, b64 + per_warp);
+  const float sx = scales[0], sm = scales[1];
+  constexpr int STEP = 32 * CMW_ROWS;
+  int nd[CMW_ROWS], nd1[CMW_ROWS];
+  float4 r[CMW_ROWS], r1[CMW_ROWS];
+  auto load = [&](int pos, int (&d)[CMW_ROWS], float4 (&q)[CMW_ROWS]) {
+#pragma unroll
+    for (int k = 0; k < CMW_ROWS; ++k) { const int i = pos + 32 * k + lane; d[k] = (i < end) ? __ldcs(nid + i) : -1; }
+#pragma unroll
+    for (int k = 0; k < CMW_ROWS; ++k) if (d[k] >= 0) q[k] = __ldcs(rec + pos + 32 * k + lane);
+  };
+  auto reduce_flush = [&](Part &p, int node) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { p.umin[q] = __reduce_min_sync(0xffffffffu, p.umin[q]); p.umax[q] = __reduce_max_sync(0xffffffffu, p.umax[q]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) p.s[q] += shfl_xor_ll(p.s[q], o);
+    }
+    if (lane == 0) {
+      NodeAcc &A = acc[node];
+      for (int k = 0; k < 3; ++k) { atomicMin(&A.umin[k], p.umin[k]); atomicMax(&A.umax[k], p.umax[k]); }
+      for (int k = 0; k < 4; ++k) add_split(&A.lo[k], &A.hi[k], p.s[k]);
+    }
+  };
+  load(begin, nd, r);
+  int K = -1;                 // node whose per-lane partial is carried in p
+  Part p; part_reset(p);
+  for (int pos = begin; pos < end; pos += STEP) {
+    load(pos + STEP, nd1, r1);         // rows past `end` load nothing
+    int mn = INT_MAX;
+#pragma unroll
+    for (int k = 0; k < CMW_ROWS; ++k) if (nd[k] >= 0) mn = min(mn, nd[k]);
+    int cur = __reduce_min_sync(0xffffffffu, mn);
+    while (cur != INT_MAX) {           // warp-uniform: the distinct nodes of this step, in increasing order
+      if (cur != K) {
+        if (K >= 0) reduce_flush(p, K);
+        part_reset(p); K = cur;
+      }
+      int next = INT_MAX;
+#pragma unroll
+      for (int k = 0; k < CMW_ROWS; ++k) {
+        if (nd[k] == cur) part_add(p, r[k], sx, sm);
+        else if (nd[k] > cur) next = min(next, nd[k]);
+      }
+      cur = __reduce_min_sync(0xffffffffu, next);
+    }
+#pragma unroll
+    for (int k = 0; k < CMW_ROWS; ++k) { nd[k] = nd1[k]; r[k] = r1[k]; }
+  }
+  if (K >= 0) reduce_flush(p, K);
 }
 
 // ---- pass B: finalize the nodes of one level, decide splits, allocate children breadth-first ----------
@@ -760,6 +827,21 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
     HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lc, k_left_count, TPB, 0));
     if (occ_lc < 1 || occ_sc < 1) { occ_lc = 0; set_error("tile kernels do not fit on an SM"); return 2; }
   }
+  // experimental k_cm_warp (HACCSR_CM_KERNEL=warp): one contiguous range of particles per resident warp
+  int cmw_per_warp = 0, cmw_blocks = 0;
+  {
+    const char *e = getenv("HACCSR_CM_KERNEL");
+    if (e && !strcmp(e, "warp") && n > 0) {
+      int occ = 0;
+      HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cm_warp, TPB, 0));
+      const long long warps = (long long)c->sm_count * (occ > 0 ? occ : 1) * (TPB / 32);
+      const int step = 32 * CMW_ROWS;
+      long long pw = ((long long)n + warps - 1) / warps;
+      pw = (pw + step - 1) / step * step;
+      cmw_per_warp = (int)pw;
+      cmw_blocks = (int)(((long long)n + pw * (TPB / 32) - 1) / (pw * (TPB / 32)));
+    }
+  }
   const int grid_lc = ntiles < c->sm_count * occ_lc ? (ntiles > 0 ? ntiles : 1) : c->sm_count * occ_lc;
   const int grid_sc = ntiles < c->sm_count * occ_sc ? (ntiles > 0 ? ntiles : 1) : c->sm_count * occ_sc;
   // node pool: every split node has > ppn particles and two non-empty children, so nodes <= 2N-1; in
@@ -808,7 +890,8 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
     for (;; ++level) {
       if (level >= 127) { set_error("tree deeper than 127 levels"); return 1; }
       c->level_begin[level] = begin; c->level_end[level] = end;
-      k_cm_tile<<<(n + CM_TILE - 1) / CM_TILE, TPB, 0, st>>>(rec, nid, n, c->acc.p, scales);
+      if (cmw_per_warp) k_cm_warp<<<cmw_blocks, TPB, 0, st>>>(rec, nid, n, cmw_per_warp, c->acc.p, scales);
+      else k_cm_tile<<<(n + CM_TILE - 1) / CM_TILE, TPB, 0, st>>>(rec, nid, n, c->acc.p, scales);
       {
         const int nl = end - begin, gb = (nl + 255) / 256;
         HSR_TRY(c->split_flag.ensure((size_t)nl + 1)); HSR_TRY(c->split_rank.ensure((size_t)nl + 1));
