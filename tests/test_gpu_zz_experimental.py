@@ -21,6 +21,7 @@ def _kick(p, b, ppn, tdpts):
         g.close()
 
 
+@pytest.mark.timeout(180)
 @pytest.mark.xfail(strict=False, reason="k_cm_warp (HACCSR_CM_KERNEL=warp): validated stand-alone only (tools/microbench_cm.cu)")
 @pytest.mark.parametrize("kind,n,ppn", [("clustered", 32, 100), ("zeld", 48, 512), ("lattice", 20, 64)])
 def test_cm_warp_kernel_builds_the_identical_tree(kind, n, ppn, monkeypatch):
