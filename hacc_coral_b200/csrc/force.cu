@@ -665,6 +665,7 @@ template <int NC, int LAW, bool GUARD0, int FUSED = 0>
 static int launch_force(haccsr_ctx *c, const ForceParams &P0, int n_items, bool count) {
   // per group of items (a single group unless haccsr_kick_host asked for range-wise velocity copies): one launch for the
   // chunk items, one for the remainder items
+  (void)n_items;       // the item ranges of the launches come from haccsr_ctx::seg_off
   const int groups = c->force_groups;
   for (int g = 0; g < groups; ++g) {
     for (int rem = 0; rem < 2; ++rem) {
