@@ -5,8 +5,12 @@ A "step" is one pass of the hot path over one sub-volume: tree build + interacti
 kernel (= one RCBForceTree constructor call of the reference, src/cpu/Particles.cxx:1313-1338).
   value     whole-job evaluated pairs per second with the particles already resident in HBM
   e2e       same, through the C ABI with HOST buffers: upload (H2D) + kick + download (D2H) per step
+            (haccsr_kick_host, the facade constructor's path); e2e.subcycle is the Level-2 path of INTEGRATION.md,
+            haccsr_upload + haccsr_subcycle(nsub) + haccsr_download: the same copies amortised over nsub kicks
   roofline  force kernel only: 30 flop per evaluated pair / its CUDA-event time,
             against the FP32 FMA peak  n_SM * 128 lanes * 2 * sm_max_mhz
+  roofline_build  tree build: N * (28 L + 84) algorithmic bytes / its CUDA-event time against the measured HBM peak
+  clustered the same measurements on configs[2] (shell-crossed snapshot), the state north_star's target names
   cpu_baseline  the reference's own compiled sources (oracle/_ref) on a bounded cut-out of the same snapshot
 `--impl reference` times that CPU reference alone (all host threads) and prints the same line shape.
 """
@@ -19,8 +23,16 @@ import threading
 import time
 
 # the CPU reference keeps its interaction lists on the stacks of its OpenMP workers (4 * VMAX floats, RCBForceTree.cxx:940);
-# libgomp reads the variable once, when the first OpenMP runtime of the process starts (torch's import), so it is set here
+# libgomp reads the variables once, when the first OpenMP runtime of the process starts (torch's import), so they are set here
 os.environ.setdefault("OMP_STACKSIZE", "64M")
+if "reference" in sys.argv:
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers when nproc > 1; the reference arm is the CPU
+    # implementation with all the host threads it can use, on rank 0 alone
+    try:
+        _ncpu = len(os.sched_getaffinity(0))
+    except Exception:
+        _ncpu = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(_ncpu)
 
 import numpy as np  # noqa: E402
 
@@ -30,6 +42,7 @@ sys.path.insert(0, ROOT)
 FLOP_PER_PAIR = 30          # poly5 law, FMA = 2, rsqrt = 1, compare/select = 0
 RSM, EDGE, THETA = 0.007, 3.2, 0.5   # reference indat:37-41
 GHOST = 11                  # overload cells per face at the shipped spacing
+STATE_NAME = {"uniform": "z=50 near-uniform", "clustered": "shell-crossed clustered", "clumpy": "shell-crossed + isothermal knots"}
 
 
 def parse():
@@ -43,15 +56,18 @@ def parse():
     ap.add_argument("--state", default="uniform", choices=["uniform", "clustered", "clumpy"],
                     help="uniform = z=50 Zel'dovich (configs[1]); clustered = shell-crossed Zel'dovich (configs[2]); clumpy = "
                          "clustered + 15 %% of the particles in 64 isothermal knots (stress case: lists beyond the reference's VMAX)")
-    ap.add_argument("--sample-side", type=int, default=112,
-                    help="cut-out side (cells) for the CPU baseline: 112^3 cells = 1.4 M particles = about 10 s on 16 cores")
+    ap.add_argument("--no-clustered-block", action="store_true",
+                    help="skip the side block 'clustered' (configs[2]) that the default uniform line carries")
+    ap.add_argument("--sample-side", type=int, default=0,
+                    help="cut-out side (cells) for the CPU baseline; 0 = sized from a calibration run so the arm stays within --cpu-budget")
+    ap.add_argument("--cpu-budget", type=float, default=100.0, help="seconds of CPU reference work allowed in total (reference arm)")
     ap.add_argument("--arith", default="fused", choices=["fused", "x86"], help="pair-kernel arithmetic (include/haccsr.h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--subcycle", type=int, default=0, metavar="NSUB",
-                    help="also time Particles::subCycle on the device (haccsr_subcycle: NSUB x [stream, out-of-box compaction, mass=1, "
-                         "kick, stream], one upload and one download) and report it as the side block 'subcycle' (configs[4])")
+    ap.add_argument("--subcycle", type=int, default=5, metavar="NSUB",
+                    help="sub-cycles per long step for the Level-2 end-to-end path (haccsr_subcycle; reference indat nsub = 5); 0 = skip")
     ap.add_argument("--cull", action="store_true", help="headline run with warp-level culling on (haccsr_set_culling); "
                     "by default culling is off and only a side measurement of it is reported under 'culled'")
+    ap.add_argument("--tune-ppn", default="", help="comma-separated leaf sizes for the side block 'tuned' (time to solution per kick)")
     return ap.parse_args()
 
 
@@ -140,43 +156,302 @@ class NumaLocal:
         return False
 
 
-def make_snapshot(args, rank, device):
+def make_snapshot(args, state, rank, device, np_side=None):
     from hacc_coral_b200 import synth
-    boost = 1.0
-    z = 50.0
-    if args.state in ("clustered", "clumpy"):
+    boost, z = 1.0, 50.0
+    if state in ("clustered", "clumpy"):
         z, boost = 0.0, 0.35      # Zel'dovich pushed to shell crossing: sheets / filaments / knots
+    side = np_side or args.np_side
     try:
-        p = synth.zeldovich_torch(args.np_side, z=z, seed=5009888 + rank, ghost=GHOST, growth_boost=boost, device=device)
+        p = synth.zeldovich_torch(side, z=z, seed=5009888 + rank, ghost=GHOST, growth_boost=boost, device=device)
     except Exception:
-        p = synth.zeldovich(args.np_side, z=z, seed=5009888 + rank, ghost=GHOST, growth_boost=boost)
-    if args.state == "clumpy":
-        synth.add_clumps(p, float(args.np_side + 2 * GHOST), seed=99 + rank)
+        p = synth.zeldovich(side, z=z, seed=5009888 + rank, ghost=GHOST, growth_boost=boost)
+    if state == "clumpy":
+        synth.add_clumps(p, float(side + 2 * GHOST), seed=99 + rank)
     return p
 
 
-def run_reference_sample(p, nglt, args):
-    """Time the compiled reference (oracle/_ref) on a cut-out of the snapshot.  Returns dict or None."""
+def run_reference_sample(p, nglt, side, ppn):
+    """Time the compiled reference (oracle/_ref) on a `side`^3-cell cut-out of the snapshot.  Returns dict or None."""
     from hacc_coral_b200 import synth
     from oracle import refbind, oraclebind
     if not refbind.available():
         return None
-    side = min(args.sample_side, nglt)
+    side = min(side, nglt)
     lo = (nglt - side) // 2
     q = synth.cutout(p, lo, lo + side)
     box = ([0.0] * 3, [float(side)] * 3, [EDGE] * 3, [float(side) - EDGE] * 3)
     # pair count of the identical call from the plain-C restatement (walk only, no force)
-    walk = oraclebind.run(q, *box, RSM, THETA, args.ppn, do_force=False)["stats"]
+    walk = oraclebind.run(q, *box, RSM, THETA, ppn, do_force=False)["stats"]
     cnt = walk["pairs_eval"]
     # the reference keeps its lists in fixed stack arrays of VMAX = 16384 entries and asserts on overflow
     # (RCBForceTree.cxx:921,1039,1070): where the cut-out's longest list comes close, the build with the #define raised
     # (oracle/build_ref.sh) is timed instead, and the sample says so
     big = walk["max_list"] >= 16000 and refbind.available(vmax=True)
     t0 = time.time()
-    _, st, _ = refbind.rcb_kick(q, *box, RSM, THETA, args.ppn, fcoeff=1.0, law=refbind.LAW_POLY5, vmax=big)
+    _, st, _ = refbind.rcb_kick(q, *box, RSM, THETA, ppn, fcoeff=1.0, law=refbind.LAW_POLY5, vmax=big)
     dt = time.time() - t0
     return {"pairs": int(cnt), "seconds": dt, "particles": int(q["x"].size), "side": side,
-            "cores": os.cpu_count(), "wall_ctor_s": st["wall_s"], "note": ", VMAX raised to 1048576" if big else ""}
+            "cores": int(os.environ.get("OMP_NUM_THREADS", 0)) or len(os.sched_getaffinity(0)),
+            "wall_ctor_s": st["wall_s"], "note": ", VMAX raised to 1048576" if big else ""}
+
+
+def reference_arm(args, config):
+    """`--impl reference`: the reference's own compiled RCBForceTree on the host cores, on a cut-out of the same snapshot
+    recipe sized so that warmup + steps repetitions stay within --cpu-budget seconds."""
+    import torch  # noqa: F401  (only for the snapshot generator's fallback path)
+    reps = args.warmup + args.steps
+    calib_side = 56
+    sub_side = min(args.np_side, 136)
+    p = make_snapshot(args, args.state, 0, "cpu", np_side=sub_side)       # a snapshot just large enough to hold any cut-out
+    nglt = sub_side + 2 * GHOST
+    info = run_reference_sample(p, nglt, calib_side, args.ppn)            # calibration, untimed
+    if info is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhaccref.so not built"}))
+        return 0
+    if args.sample_side > 0:
+        side = args.sample_side
+    else:
+        per_particle = info["seconds"] / max(info["particles"], 1)
+        budget = max(args.cpu_budget - 1.5 * info["seconds"], 5.0) / max(reps, 1)
+        side = int(max(48, min(nglt, (budget / per_particle) ** (1.0 / 3.0))))
+        side -= side % 8
+    vals = []
+    for it in range(reps):
+        info = run_reference_sample(p, nglt, side, args.ppn)
+        if it >= args.warmup:
+            vals.append(info["pairs"] / info["seconds"] / 1e9)
+    v = float(np.mean(vals))
+    sample = "SAMPLED: %d^3-cell cut-out (%d particles, %d pairs) of the same snapshot recipe, full RCBMonopoleForceTree ctor%s, %d OpenMP threads" % (
+        info["side"], info["particles"], info["pairs"], info["note"], info["cores"])
+    line = {"metric": "short-range G interactions/s", "value": v, "unit": "Ginteractions/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * info["seconds"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "impl": "reference", "cpu_baseline": {"value": v, "unit": "Ginteractions/s", "cores": info["cores"],
+                                                  "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "Ginteractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+class Bench:
+    """One rank's measurements on one snapshot."""
+
+    def __init__(self, args, rank, world, local, dist):
+        import torch
+        import hacc_coral_b200 as H
+        self.torch, self.H, self.args, self.rank, self.world, self.local, self.dist = torch, H, args, rank, world, local, dist
+        self.dev = "cuda:%d" % local
+        self.nglt = args.np_side + 2 * GHOST
+        self.lo, self.hi = [0.0] * 3, [float(self.nglt)] * 3
+        self.flo, self.fhi = [EDGE] * 3, [float(self.nglt) - EDGE] * 3
+        self.stream = torch.cuda.current_stream()
+        self.g = None
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def events(self, k):
+        return [self.torch.cuda.Event(enable_timing=True) for _ in range(k)]
+
+    def load(self, state):
+        """Generate the snapshot of `state`, page-lock it, create the context and upload."""
+        torch, H, args = self.torch, self.H, self.args
+        if self.g is not None:
+            self.g.close()
+        self.p = make_snapshot(args, state, self.rank, self.dev)
+        self.n = int(self.p["x"].size)
+        with NumaLocal(self.local):
+            self.pin = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in self.p.items()}
+            self.work = {k: torch.from_numpy(v.copy()).pin_memory().numpy() for k, v in self.p.items()}
+        g = H.HaccSR(self.n, device=self.local, arith=H.ARITH_FUSED if args.arith == "fused" else H.ARITH_X86)
+        g.set_force_law(H.LAW_SR_POLY, H.POLY5, RSM, H.RMAX)
+        g.set_culling(args.cull)
+        g.set_stream(self.stream.cuda_stream)
+        g.upload(self.pin)
+        self.g = g
+
+    def kick(self, ppn=None, **kw):
+        return self.g.kick(self.lo, self.hi, self.flo, self.fhi, THETA, ppn or self.args.ppn, **kw)
+
+    def resident(self, steps, warmup, sampler=None):
+        """`steps` kicks on resident particles between two events (after `warmup` untimed ones)."""
+        for _ in range(warmup):
+            st = self.kick()
+        self.barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = self.events(2)
+        e0.record(self.stream)
+        acc = {"pairs": 0, "ms_force": 0.0, "ms_build": 0.0, "ms_walk": 0.0, "launches": 0, "force_launches": 0}
+        for _ in range(steps):
+            st = self.kick()
+            acc["pairs"] += st["pairs_evaluated"]
+            acc["ms_force"] += st["ms_force"]; acc["ms_build"] += st["ms_build"]; acc["ms_walk"] += st["ms_walk"]
+            acc["launches"] += st["total_launches"]; acc["force_launches"] += st["force_launches"]
+        e1.record(self.stream)
+        self.barrier()
+        if sampler:
+            sampler.stop_flag = True
+        acc["ms"] = e0.elapsed_time(e1)
+        acc["steps"] = steps
+        acc["st"] = st
+        return acc
+
+    def e2e_facade(self, steps):
+        """haccsr_kick_host on caller-owned page-locked arrays = H2D of all ten arrays + build + walk + force + D2H of all
+        ten arrays, every step.  The arrays are kicked in place (each step starts from the previous step's output)."""
+        self.g.kick_host(self.work, self.lo, self.hi, self.flo, self.fhi, THETA, self.args.ppn)   # warm
+        self.barrier()
+        e0, e1 = self.events(2)
+        e0.record(self.stream)
+        pairs = 0
+        for _ in range(steps):
+            st = self.g.kick_host(self.work, self.lo, self.hi, self.flo, self.fhi, THETA, self.args.ppn)
+            pairs += st["pairs_evaluated"]
+        e1.record(self.stream)
+        self.barrier()
+        return {"pairs": pairs, "ms": e0.elapsed_time(e1), "steps": steps}
+
+    def e2e_subcycle(self, nsub, reps):
+        """Level-2 path: one haccsr_upload, haccsr_subcycle(nsub) = nsub x [stream, out-of-box compaction, mass = 1, kick,
+        stream] on the device, one haccsr_download (reference src/cpu/Particles.cxx:1176-1201)."""
+        vmax = max(float(np.abs(self.pin[k]).max()) for k in ("vx", "vy", "vz"))
+        # each half-stream moves the fastest particle 0.02 cells; the parity snapshots carry v = 0, then only the kicks move them
+        pt = 0.02 / vmax if vmax > 0 else 0.01
+        sub_args = (nsub, pt, [float(self.nglt)] * 3, self.lo, self.hi, self.flo, self.fhi, THETA, self.args.ppn, 1e-3)
+        self.g.upload(self.pin)
+        self.g.subcycle(*sub_args)                         # warm
+        self.barrier()
+        e = self.events(2)
+        e[0].record(self.stream)
+        pairs, ms_res = 0, 0.0
+        for _ in range(reps):
+            s = self.events(2)
+            self.g.upload(self.pin)
+            s[0].record(self.stream)
+            sst = self.g.subcycle(*sub_args)
+            s[1].record(self.stream)
+            self.g.download(out=self.work)
+            pairs += sst["pairs_evaluated"]
+            self.torch.cuda.synchronize()
+            ms_res += s[0].elapsed_time(s[1])
+        e[1].record(self.stream)
+        self.barrier()
+        out = {"pairs": pairs, "ms": e[0].elapsed_time(e[1]), "ms_resident": ms_res, "reps": reps, "nsub": nsub}
+        self.g.upload(self.pin)
+        return out
+
+    def pcie(self):
+        """Host<->device copy rates of the ten arrays with every rank copying at the same time."""
+        self.barrier()
+        e = self.events(3)
+        e[0].record(self.stream)
+        self.g.upload(self.pin)
+        e[1].record(self.stream)
+        self.g.download(out=self.work)
+        e[2].record(self.stream)
+        self.barrier()
+        b = 42.0 * self.n
+        return b / (e[0].elapsed_time(e[1]) * 1e-3) / 1e9, b / (e[1].elapsed_time(e[2]) * 1e-3) / 1e9
+
+    def culled(self, base_ms_force):
+        """The same kick with warp-level culling toggled (bit-identical result, fewer executed flops)."""
+        args = self.args
+        self.g.set_culling(not args.cull)
+        self.kick()
+        other = [self.kick() for _ in range(3)]
+        oc = self.kick(count_in_cutoff=True)
+        # end to end through the facade path with culling on
+        e2e = self.e2e_facade(2)
+        self.g.set_culling(args.cull)
+        self.g.upload(self.pin)
+        oms = float(np.mean([o["ms_force"] for o in other]))
+        on_ms, off_ms = (base_ms_force, oms) if args.cull else (oms, base_ms_force)
+        return {"ms_force": on_ms, "ms_force_unculled": off_ms, "speedup_force": off_ms / on_ms,
+                "ms_kick": float(np.mean([o["ms_total"] for o in other])),
+                "pairs_force_law_frac": oc["pairs_force_law"] / max(oc["pairs_evaluated"], 1),
+                "frac_executed_flop": (30.0 * oc["pairs_force_law"] + 9.0 * (oc["pairs_evaluated"] - oc["pairs_force_law"]))
+                / (30.0 * max(oc["pairs_evaluated"], 1)),
+                "e2e": {"value": e2e["pairs"] / (e2e["ms"] * 1e-3) / 1e9, "unit": "Ginteractions/s", "ms_per_step": e2e["ms"] / e2e["steps"],
+                        "note": "haccsr_kick_host with culling %s, this rank" % ("off" if args.cull else "on")},
+                "note": "warp-level early exit after the cutoff test; results bit-identical; off in the headline unless --cull"}
+
+    def tuned(self, ppns, ref_pairs_incut):
+        """Time to solution per kick for other leaf sizes (-N of the reference, src/simulation/MC3Options.cxx:91-136):
+        the same physical in-cutoff pairs, fewer list pairs evaluated."""
+        rows = []
+        for ppn in ppns:
+            self.kick(ppn=ppn)
+            ks = [self.kick(ppn=ppn) for _ in range(3)]
+            kc = self.kick(ppn=ppn, count_in_cutoff=True)
+            ms = float(np.mean([k["ms_total"] for k in ks])); msf = float(np.mean([k["ms_force"] for k in ks]))
+            rows.append({"ppn": ppn, "ms_kick": ms, "ms_force": msf, "ms_build": float(np.mean([k["ms_build"] for k in ks])),
+                         "pairs_evaluated": int(kc["pairs_evaluated"]), "pairs_in_cutoff": int(kc["pairs_in_cutoff"]),
+                         "in_cutoff_Gpairs_per_s": kc["pairs_in_cutoff"] / (ms * 1e-3) / 1e9,
+                         "roofline_frac": FLOP_PER_PAIR * kc["pairs_evaluated"] / (msf * 1e-3) / 1e12 / self.fp32_peak,
+                         "levels": int(kc["levels"]), "mean_ppn": kc["mean_ppn"]})
+        return rows
+
+
+def block_for_state(B, args, steps, warmup, world, sampler=None):
+    """Everything measured on the currently loaded snapshot; returns (local dict, reducible numbers)."""
+    torch = B.torch
+    acc = B.resident(steps, warmup, sampler)
+    e2e = B.e2e_facade(max(1, min(steps, 3)))
+    B.g.upload(B.pin)
+    sub = B.e2e_subcycle(args.subcycle, 2 if steps > 2 else 1) if args.subcycle > 0 else None
+    h2d, d2h = B.pcie()
+    stc = B.kick(count_in_cutoff=True)     # one untimed pass that also counts the pairs inside the cutoff
+    tv = [acc["ms"], e2e["ms"], sub["ms"] if sub else 0.0, -h2d, -d2h]
+    sv = [float(acc["pairs"]), float(e2e["pairs"]), float(sub["pairs"]) if sub else 0.0, float(acc["launches"])]
+    tvt = torch.tensor(tv, device=B.dev, dtype=torch.float64)
+    svt = torch.tensor(sv, device=B.dev, dtype=torch.float64)
+    if B.dist is not None:
+        B.dist.all_reduce(tvt, op=B.dist.ReduceOp.MAX)
+        B.dist.all_reduce(svt, op=B.dist.ReduceOp.SUM)
+    tv = [float(t) for t in tvt.cpu()]
+    sv = [float(t) for t in svt.cpu()]
+    st, n = acc["st"], B.n
+    pk, pk_kind = peaks()
+    achieved = FLOP_PER_PAIR * acc["pairs"] / (acc["ms_force"] * 1e-3) / 1e12          # this rank's force kernel
+    L = int(st["levels"])
+    alg_bytes = n * (28.0 * L + 84.0)                 # SURVEY.md 8(d): L * (16 B box/COM read + 4 B key read + 8 B index r/w) + 84 B
+    ms_build = acc["ms_build"] / steps
+    hbm = float(pk.get("hbm_gbs", 6650.0))
+    out = {
+        "value": sv[0] / (tv[0] * 1e-3) / 1e9, "ms_per_step": tv[0] / steps,
+        "e2e": {"value": sv[1] / (tv[1] * 1e-3) / 1e9, "unit": "Ginteractions/s", "h2d_bytes_per_step": 42 * n, "d2h_bytes_per_step": 42 * n,
+                "ms_per_step": tv[1] / e2e["steps"], "path": "haccsr_kick_host (facade constructor: all ten arrays up and down every kick)",
+                "pcie_gbs_per_gpu_min_over_ranks": {"h2d": -tv[3], "d2h": -tv[4], "note": "haccsr_upload / haccsr_download of the ten arrays, all ranks copying at once"}},
+        "gpu_launches": int(sv[3]),
+        "roofline": {"bound": "fp32", "kernel": "k_force", "achieved": achieved, "peak": B.fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / B.fp32_peak, "traffic": ncu_traffic("k_force", args.np_side, B.state, args.arith),
+                     "peak_source": B.peak_source, "flop_per_interaction": FLOP_PER_PAIR,
+                     "ms_per_launch": acc["ms_force"] / max(acc["force_launches"], 1)},
+        "roofline_build": {"bound": "hbm", "kernel": "tree build (k_split_pass per level + k_gather)",
+                           "achieved": alg_bytes / (ms_build * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                           "frac": alg_bytes / (ms_build * 1e-3) / 1e9 / hbm, "algorithmic_bytes": alg_bytes,
+                           "bytes_per_particle": "28 * levels + 84 (SURVEY.md 8(d))", "levels": L, "ms": ms_build,
+                           "traffic": ncu_traffic("build", args.np_side, B.state, args.arith), "peak_source": pk_kind + " hbm_gbs"},
+        "phases_ms": {"build": ms_build, "walk": acc["ms_walk"] / steps, "force": acc["ms_force"] / steps},
+        "particles_per_gpu": n, "pairs_per_particle": st["pairs_evaluated"] / n,
+        "pairs_in_cutoff_frac": stc["pairs_in_cutoff"] / max(stc["pairs_evaluated"], 1),
+        "tree": {"nodes": st["nodes"], "leaves": st["leaves"], "mean_ppn": st["mean_ppn"], "levels": st["levels"],
+                 "max_list": st["max_list"], "pseudo_particles": st["pseudo_particles"]},
+    }
+    if sub:
+        kicks = sub["reps"] * sub["nsub"]
+        out["e2e"]["subcycle"] = {
+            "value": sv[2] / (tv[2] * 1e-3) / 1e9, "unit": "Ginteractions/s", "nsub": sub["nsub"], "ms_per_kick": tv[2] / kicks,
+            "h2d_bytes_per_kick": 42 * n // sub["nsub"], "d2h_bytes_per_kick": 42 * n // sub["nsub"],
+            "ms_per_kick_resident_this_rank": sub["ms_resident"] / kicks,
+            "path": "haccsr_upload + haccsr_subcycle(nsub) + haccsr_download (INTEGRATION.md Level 2 = Particles::subCycle, Particles.cxx:1176-1201)"}
+    return out, acc, stc
 
 
 def main():
@@ -185,45 +460,21 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     nglt = args.np_side + 2 * GHOST
-    workload = "np=%d^3 alive per GPU + %d-cell overload shell (%d^3 grid units), %s Zel'dovich snapshot, ppn=%d, theta=%.1f, poly5" % (
-        args.np_side, GHOST, nglt, {"uniform": "z=50 near-uniform", "clustered": "shell-crossed clustered", "clumpy": "shell-crossed + isothermal knots"}[args.state], args.ppn, THETA)
-    config = {"workload": workload, "np_side": args.np_side, "ppn": args.ppn, "theta": THETA, "rsm": RSM,
-              "force_law": "poly5", "arithmetic": args.arith, "state": args.state, "l2": "inputs larger than L2 (no flush needed)",
-              "parallelism": "1 sub-volume per GPU, no data-path collective"}
+
+    def config_for(state):
+        workload = "np=%d^3 alive per GPU + %d-cell overload shell (%d^3 grid units), %s Zel'dovich snapshot, ppn=%d, theta=%.1f, poly5" % (
+            args.np_side, GHOST, nglt, STATE_NAME[state], args.ppn, THETA)
+        return {"workload": workload, "np_side": args.np_side, "ppn": args.ppn, "theta": THETA, "rsm": RSM,
+                "force_law": "poly5", "arithmetic": args.arith, "state": state, "l2": "inputs larger than L2 (no flush needed)",
+                "parallelism": "1 sub-volume per GPU, no data-path collective"}
+    config = config_for(args.state)
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        import torch  # noqa: F401  (only for the snapshot generator's fallback path)
-        # the reference arm only needs the cut-out: a snapshot of the same recipe (spacing, redshift, seed)
-        # just large enough to contain it is generated on the CPU instead of the full field
-        sub = argparse.Namespace(**vars(args))
-        sub.np_side = min(args.np_side, max(64, args.sample_side + 8))
-        p = make_snapshot(sub, 0, "cpu")
-        vals = []
-        info = None
-        for it in range(args.warmup + args.steps):
-            info = run_reference_sample(p, sub.np_side + 2 * GHOST, args)
-            if info is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhaccref.so not built"}))
-                return 0
-            if it >= args.warmup:
-                vals.append(info["pairs"] / info["seconds"] / 1e9)
-        v = float(np.mean(vals))
-        sample = "%d^3-cell cut-out (%d particles, %d pairs) of the same snapshot recipe, full RCBMonopoleForceTree ctor%s" % (
-            info["side"], info["particles"], info["pairs"], info["note"])
-        line = {"metric": "short-range G interactions/s", "value": v, "unit": "Ginteractions/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * info["seconds"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "impl": "reference", "cpu_baseline": {"value": v, "unit": "Ginteractions/s", "cores": info["cores"],
-                                                      "kind": "reference", "sample": sample},
-                "e2e": {"value": v, "unit": "Ginteractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
-        return 0
+        return reference_arm(args, config)
 
     import torch
-    import hacc_coral_b200 as H
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device; libhaccsr has no CPU fallback"}))
         return 1
@@ -232,158 +483,53 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = "cuda:%d" % local
-    p = make_snapshot(args, rank, dev)
-    n = int(p["x"].size)
-    # pinned host copies (the caller's arrays in the e2e path)
-    pin = {}
-    with NumaLocal(local):
-        for k, v in p.items():
-            t = torch.from_numpy(v).pin_memory()
-            pin[k] = t.numpy()
-    g = H.HaccSR(n, device=local, arith=H.ARITH_FUSED if args.arith == "fused" else H.ARITH_X86)
-    g.set_force_law(H.LAW_SR_POLY, H.POLY5, RSM, H.RMAX)
-    g.set_culling(args.cull)
-    stream = torch.cuda.current_stream()
-    g.set_stream(stream.cuda_stream)
-    lo, hi = [0.0] * 3, [float(nglt)] * 3
-    flo, fhi = [EDGE] * 3, [float(nglt) - EDGE] * 3
-    g.upload(pin)
+    B = Bench(args, rank, world, local, dist)
+    pk, pk_kind = peaks()
+    props = torch.cuda.get_device_properties(local)
+    sm_max = float(pk.get("sm_max_mhz", 1965.0))
+    B.fp32_peak = props.multi_processor_count * 128 * 2 * sm_max * 1e6 / 1e12     # TFLOP/s
+    B.peak_source = "%d SMs x 128 lanes x 2 x %.0f MHz (%s sm_max_mhz)" % (props.multi_processor_count, sm_max, pk_kind)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---- resident-input throughput -----------------------------------------------------------------
-    for _ in range(args.warmup):
-        st = g.kick(lo, hi, flo, fhi, THETA, args.ppn)
+    # ---- headline state ------------------------------------------------------------------------------
+    B.state = args.state
+    B.load(args.state)
     sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    pairs = 0
-    ms_force = ms_build = ms_walk = 0.0
-    launches = force_launches = 0
-    for _ in range(args.steps):
-        st = g.kick(lo, hi, flo, fhi, THETA, args.ppn)
-        pairs += st["pairs_evaluated"]
-        ms_force += st["ms_force"]; ms_build += st["ms_build"]; ms_walk += st["ms_walk"]
-        launches += st["total_launches"]; force_launches += st["force_launches"]
-    e1.record(stream)
-    barrier()
-    sampler.stop_flag = True
-    ms = e0.elapsed_time(e1)
-    # ---- end-to-end through the C ABI with host buffers ------------------------------------------------
-    # the call a user of the reference's constructor makes: haccsr_kick_host on caller-owned (page-locked) host
-    # arrays = H2D of all ten arrays + build + walk + force + D2H of all ten arrays, every step.  The arrays are
-    # kicked in place, so each step starts from the previous step's output (same particles, tree order).
-    with NumaLocal(local):
-        work = {k: torch.from_numpy(v.copy()).pin_memory().numpy() for k, v in pin.items()}
-    g.kick_host(work, lo, hi, flo, fhi, THETA, args.ppn)   # warm
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    e2e_steps = max(1, min(args.steps, 3))
-    pairs_e2e = 0
-    for _ in range(e2e_steps):
-        st2 = g.kick_host(work, lo, hi, flo, fhi, THETA, args.ppn)
-        pairs_e2e += st2["pairs_evaluated"]
-    e3.record(stream)
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
-    g.upload(pin)
-    # one untimed pass that also counts the pairs inside the cutoff (honest-metric companion number)
-    stc = g.kick(lo, hi, flo, fhi, THETA, args.ppn, count_in_cutoff=True)
-    # side measurement: the same kick with warp-level culling (bit-identical result, fewer executed flops)
-    culled = None
-    if args.arith == "fused":
-        g.set_culling(not args.cull)
-        g.kick(lo, hi, flo, fhi, THETA, args.ppn)
-        other = [g.kick(lo, hi, flo, fhi, THETA, args.ppn) for _ in range(3)]
-        oc = g.kick(lo, hi, flo, fhi, THETA, args.ppn, count_in_cutoff=True)
-        g.set_culling(args.cull)
-        on, off_ms = (stc, np.mean([o["ms_force"] for o in other])) if args.cull else (oc, ms_force / args.steps)
-        on_ms = ms_force / args.steps if args.cull else np.mean([o["ms_force"] for o in other])
-        culled = {"ms_force": float(on_ms), "ms_force_unculled": float(off_ms), "speedup_force": float(off_ms / on_ms),
-                  "pairs_force_law_frac": on["pairs_force_law"] / max(on["pairs_evaluated"], 1),
-                  "note": "warp-level early exit after the cutoff test; results bit-identical; off in the headline unless --cull"}
+    head, acc, stc = block_for_state(B, args, args.steps, args.warmup, world, sampler)
+    culled = B.culled(acc["ms_force"] / args.steps) if args.arith == "fused" else None
+    tuned = None
+    if args.tune_ppn:
+        tuned = B.tuned([int(t) for t in args.tune_ppn.split(",")], stc["pairs_in_cutoff"])
+    p_head, nglt_head = B.p, B.nglt
 
-    # side measurement: the full short-range sub-cycle loop of one long step, particles resident between the kicks
-    subc = None
-    if args.subcycle > 0:
-        vmax = max(float(np.abs(pin[k]).max()) for k in ("vx", "vy", "vz"))
-        # each half-stream moves the fastest particle 0.02 cells; the parity snapshots carry v = 0, then only the kicks move them
-        pt = 0.02 / vmax if vmax > 0 else 0.01
-        sub_args = (args.subcycle, pt, [float(nglt)] * 3, lo, hi, flo, fhi, THETA, args.ppn, 1e-3)
-        g.upload(pin)
-        g.subcycle(*sub_args)                         # warm
-        barrier()
-        s0, s1, s2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        s0.record(stream)
-        g.upload(pin)
-        s1.record(stream)
-        sst = g.subcycle(*sub_args)
-        s2.record(stream)
-        g.download(out=work)
-        s3 = torch.cuda.Event(enable_timing=True)
-        s3.record(stream)
-        barrier()
-        subc = {"nsub": args.subcycle, "ms_resident": s1.elapsed_time(s2), "ms_with_transfers": s0.elapsed_time(s3),
-                "pairs_evaluated": int(sst["pairs_evaluated"]), "ms_force": sst["ms_force"], "ms_build": sst["ms_build"],
-                "value": sst["pairs_evaluated"] / (s1.elapsed_time(s2) * 1e-3) / 1e9,
-                "e2e_value": sst["pairs_evaluated"] / (s0.elapsed_time(s3) * 1e-3) / 1e9, "unit": "Ginteractions/s",
-                "note": "haccsr_subcycle = Particles::subCycle (Particles.cxx:1176-1201) on the device; rank 0's numbers"}
-        g.upload(pin)
+    # ---- the clustered target state as a side block (configs[2]) -------------------------------------------
+    clustered = None
+    if args.state == "uniform" and not args.no_clustered_block:
+        B.state = "clustered"
+        B.load("clustered")
+        steps_c = max(1, min(args.steps, 5))
+        clustered, acc_c, _ = block_for_state(B, args, steps_c, 3, world)
+        clustered["config"] = config_for("clustered")
+        clustered["steps"] = steps_c
+        if args.arith == "fused":
+            clustered["culled"] = B.culled(acc_c["ms_force"] / steps_c)
+    B.g.close()
 
-    tv = torch.tensor([ms, ms_e2e, ms_force], device=dev, dtype=torch.float64)
-    sv = torch.tensor([float(pairs), float(pairs_e2e), float(launches)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sv, op=dist.ReduceOp.SUM)
-    ms_max, ms_e2e_max, ms_force_max = [float(t) for t in tv.cpu()]
-    pairs_all, pairs_e2e_all, launches_all = [float(t) for t in sv.cpu()]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    pk, pk_kind = peaks()
-    props = torch.cuda.get_device_properties(local)
-    sm_max = float(pk.get("sm_max_mhz", 1965.0))
-    fp32_peak = props.multi_processor_count * 128 * 2 * sm_max * 1e6 / 1e12     # TFLOP/s
-    achieved = FLOP_PER_PAIR * pairs / (ms_force * 1e-3) / 1e12                   # rank 0's force kernel
-    value = pairs_all / (ms_max * 1e-3) / 1e9
-    e2e_v = pairs_e2e_all / (ms_e2e_max * 1e-3) / 1e9
-    bytes_pp = 42
-    build_bytes = st["levels"] * 88.0 * n + 84.0 * n     # 88 B/particle/level + final gather
-    line = {
-        "metric": "short-range G interactions/s", "value": value, "unit": "Ginteractions/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_v, "unit": "Ginteractions/s", "h2d_bytes_per_step": bytes_pp * n, "d2h_bytes_per_step": bytes_pp * n,
-                "ms_per_step": ms_e2e_max / e2e_steps},
-        "gpu_launches": int(launches_all),
-        "roofline": {"bound": "fp32", "kernel": "k_force", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp32_peak, "traffic": ncu_traffic("k_force", args.np_side, args.state, args.arith), "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (%s sm_max_mhz)" % (
-                         props.multi_processor_count, sm_max, pk_kind),
-                     "flop_per_interaction": FLOP_PER_PAIR, "ms_per_launch": ms_force / max(force_launches, 1)},
-        "roofline_build": {"bound": "hbm", "kernel": "tree build (k_cm_tile + k_left_count + k_scatter + k_gather)",
-                           "achieved": build_bytes / (ms_build / args.steps * 1e-3) / 1e9, "peak": pk.get("hbm_gbs"),
-                           "unit": "GB/s", "frac": build_bytes / (ms_build / args.steps * 1e-3) / 1e9 / pk.get("hbm_gbs", 6650.0)},
-        "phases_ms": {"build": ms_build / args.steps, "walk": ms_walk / args.steps, "force": ms_force / args.steps},
-        "particles_per_gpu": n, "pairs_per_particle": st["pairs_evaluated"] / n,
-        "pairs_in_cutoff_frac": stc["pairs_in_cutoff"] / max(stc["pairs_evaluated"], 1),
-        "tree": {"nodes": st["nodes"], "leaves": st["leaves"], "mean_ppn": st["mean_ppn"], "levels": st["levels"],
-                 "max_list": st["max_list"], "pseudo_particles": st["pseudo_particles"]},
-        "clocks": sampler.summary(),
-    }
+    line = {"metric": "short-range G interactions/s", "value": head.pop("value"), "unit": "Ginteractions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": head.pop("ms_per_step"), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config}
+    line.update(head)
+    line["clocks"] = sampler.summary()
     if culled:
         line["culled"] = culled
-    if subc:
-        line["subcycle"] = subc
+    if tuned:
+        line["tuned"] = tuned
+    if clustered:
+        line["clustered"] = clustered
     if args.cull:
         # with culling the kernel executes 30 flop only for the pairs that reach the force law and 9 (three differences,
         # the r2 chain, the softening add) for the rest: report the executed rate next to the algorithmic one
@@ -393,7 +539,7 @@ def main():
         line["config"]["culling"] = "on"
     if not args.no_cpu_baseline and world == 1:      # the contract: rank 0 at N = 1 only (the reference arm covers every N)
         try:
-            info = run_reference_sample(p, nglt, args)
+            info = run_reference_sample(p_head, nglt_head, 112, args.ppn)
         except Exception as ex:   # the baseline is a reported companion number; never fail the GPU line
             info = None
             line["cpu_baseline_error"] = repr(ex)
@@ -401,10 +547,10 @@ def main():
             line["cpu_baseline"] = {
                 "value": info["pairs"] / info["seconds"] / 1e9, "unit": "Ginteractions/s", "cores": info["cores"],
                 "kind": "reference",
-                "sample": "%d^3-cell cut-out (%d particles, %d pairs) of rank 0's snapshot, full RCBMonopoleForceTree ctor%s, %.1f s" % (
+                "sample": "SAMPLED: %d^3-cell cut-out (%d particles, %d pairs) of rank 0's snapshot, full RCBMonopoleForceTree ctor%s, %.1f s" % (
                     info["side"], info["particles"], info["pairs"], info["note"], info["seconds"])}
     print(json.dumps(line))
-    g.close()
+    sys.stdout.flush()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -146,8 +146,8 @@ int haccsr_create(haccsr_ctx **out, int device, int64_t max_particles) {
     c->stream = c->own_stream;
     if ((rc = alloc_soa(c->cur, max_particles))) break;
     if ((rc = alloc_soa(c->alt, max_particles))) break;
-    if (cudaMallocHost((void **)&c->h_level, sizeof(LevelInfo)) != cudaSuccess) { rc = 2; break; }
-    if (cudaMalloc((void **)&c->d_level, sizeof(LevelInfo)) != cudaSuccess) { rc = 2; break; }
+    if (cudaMallocHost((void **)&c->h_state, sizeof(BuildState)) != cudaSuccess) { rc = 2; break; }
+    if (cudaMalloc((void **)&c->d_state, sizeof(BuildState)) != cudaSuccess) { rc = 2; break; }
     if (cudaMallocHost((void **)&c->h_counters, 32 * sizeof(int64_t)) != cudaSuccess) { rc = 2; break; }
     if (cudaMalloc((void **)&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) { rc = 2; break; }
     for (int i = 0; i < 5; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { rc = 2; break; }
@@ -174,13 +174,13 @@ int haccsr_destroy(haccsr_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_soa(c->cur); free_soa(c->alt);
   c->recA.release(); c->recB.release(); c->src4.release(); c->idxA.release(); c->idxB.release(); c->perm.release();
-  c->nidA.release(); c->nidB.release(); c->nodes.release(); c->acc.release(); c->lstart.release(); c->lend.release();
-  c->lbase.release(); c->nleft.release(); c->tilecount.release(); c->tilebase.release(); c->scratch_u32.release();
+  c->nidA.release(); c->nidB.release(); c->nodes.release(); c->acc.release(); c->tot.release(); c->tile_desc.release();
+  c->node_desc.release(); c->tilecount.release(); c->tilebase.release(); c->scratch_u32.release();
   c->n_ranges.release(); c->n_pseudo.release(); c->range_off.release(); c->pseudo_off.release(); c->list_len.release();
   c->ranges.release(); c->pool.release(); c->law_table.release(); c->item_cnt.release(); c->item_off.release(); c->items.release(); c->items_sorted.release(); c->lpt_hist.release(); c->refresh_slots.release();
-  c->scan_tmp.release(); c->pp12.release(); c->split_flag.release(); c->split_rank.release(); c->cic_acc.release(); c->cic_grid.release();
-  if (c->h_level) cudaFreeHost(c->h_level);
-  if (c->d_level) cudaFree(c->d_level);
+  c->scan_tmp.release(); c->pp12.release(); c->cic_acc.release(); c->cic_grid.release();
+  if (c->h_state) cudaFreeHost(c->h_state);
+  if (c->d_state) cudaFree(c->d_state);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->d_counters) cudaFree(c->d_counters);
   for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);

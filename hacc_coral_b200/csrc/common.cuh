@@ -87,12 +87,19 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-// Per-level bookkeeping written by the device and read by the host after each level.
-struct LevelInfo {
-  int begin, end;     // node index range of the NEXT level
-  int nsplit;         // nodes split at this level
-  int error;          // 1 = node pool exhausted
-  int unit_mass;      // written with the root: 1 = every particle mass is exactly 1.0f
+// Exact centroid sums of a finished node (128-bit two's complement, low and high word): a right child's sums are its
+// parent's minus its left sibling's.
+struct NodeTot {
+  unsigned long long lo[4], hi[4];
+};
+
+// Build bookkeeping kept on the device so that the levels can be queued without a host round trip (tree_build.cu).
+struct BuildState {
+  int error;                            // 1 = node pool exhausted
+  int unit_mass;                        // written with the root: 1 = every particle mass is exactly 1.0f
+  unsigned tile_ticket, node_ticket;    // tile / node-block tickets of the running launch
+  int nsplit[128];                      // nodes split at each level (-1 = level not reached, 0 = the tree ends here)
+  int lvl_begin[129], lvl_end[129];     // node index range of each level
 };
 
 // no_pseudo bit 0: the node's list holds real particles only; bit 1: remainder item (sources over lanes, force.cu)
@@ -121,13 +128,13 @@ struct haccsr_ctx {
   haccsr::DevBuf<haccsr::NodeAcc> acc;
   haccsr::DevBuf<float4> pp12;                      // TDPTS = 12: the 12 pseudo-particles (x,y,z,m) of every node
   int tdpts = 1;                                    // pseudo-particles per accepted node of the last build (1 or 12)
-  haccsr::DevBuf<int> lstart, lend, lbase, nleft;   // per node: local prefixes at first / last particle, L(o_k), is_k
-  haccsr::DevBuf<unsigned> tilecount, tilebase;     // per tile: left count, exclusive scan
-  haccsr::DevBuf<unsigned> split_flag, split_rank;  // per node of the current level: splits (0/1), exclusive scan
+  haccsr::DevBuf<haccsr::NodeTot> tot;              // exact centroid sums of every finished node
+  haccsr::DevBuf<unsigned long long> tile_desc, node_desc;   // look-back descriptors: per tile (split pass), per block (node kernel)
+  haccsr::DevBuf<unsigned> tilecount, tilebase;     // per tile: counts and their exclusive scan (refresh.cu)
   haccsr::DevBuf<unsigned> scratch_u32;             // maxima for the fixed-point scales etc.
   haccsr::DevBuf<unsigned> scan_tmp;                // scan_exclusive on long inputs: per-block sums and their scan
-  haccsr::LevelInfo *h_level = nullptr;             // pinned
-  haccsr::LevelInfo *d_level = nullptr;
+  haccsr::BuildState *h_state = nullptr;            // pinned
+  haccsr::BuildState *d_state = nullptr;
   int64_t *h_counters = nullptr;                    // pinned, misc read-backs
   unsigned long long *d_counters = nullptr;
 

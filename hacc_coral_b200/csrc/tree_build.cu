@@ -7,20 +7,19 @@
 // particles with key < pivot going left (:640); a split that leaves one side empty keeps the node as an
 // oversized leaf with two orphan children (:727-729).
 //
-// How it is computed is not the reference's recursion.  All nodes of one level are processed together by
-// passes over fixed 1024-particle tiles (HBM-bound streaming kernels):
-//   A  k_cm_tile        per-warp box / centroid sums by node run -> per-block slots -> per-node accumulators
-//   B  k_level_finalize  one block: box, centroid, split decision, BFS child allocation (prefix scan)
-//   C1 k_left_count     per-tile count of "goes left" flags + local prefixes at node boundaries
-//   C2 k_scan           exclusive scan of tile counts  => global prefix L(i) of left flags
-//   B2 k_set_children   per node: is = L(end) - L(begin); child counts / offsets; degenerate splits
-//   C3 k_scatter        stable two-way partition of (x,y,z,m | index) records into the other buffer;
-//                       particles of finished leaves are written once to the final tree-order arrays.
+// How it is computed is not the reference's recursion.  All nodes of one level are processed together, one streaming
+// pass over the particles per level (HBM-bound), with no host round trip between levels:
+//   k_cm_tile      (root only) box / centroid sums
+//   k_level_nodes  per node of the level: box, centroid, split decision; breadth-first child allocation (block scan +
+//                  look-back over the blocks); the range of the next level goes to BuildState on the device
+//   k_split_pass   per particle: left flag, rank among the node's left / right particles (segmented tile scan + decoupled
+//                  look-back over the tiles), move to the other record buffer, and the box / centroid sums of the child it
+//                  lands in; particles of finished leaves are written once to the final tree-order arrays
 // The centroid sums are accumulated as wide fixed-point integers (two 64-bit words, add_split), so they are exact and independent
 // of summation order: the build is deterministic, and the float centroid equals the reference's
 // (double-accumulated) one except where the reference's own rounding error straddles a float boundary.
 // Children are numbered breadth-first (parent index < child index, as the reference guarantees at :808-809).
-// Left blocks keep input order like the reference; right blocks are kept stable too (the reference's
+// Left blocks keep input order like the reference; right blocks are written back to front (the reference's
 // right-block order is an artefact of its swap loop and only affects FP32 summation order).
 #include "common.cuh"
 
@@ -116,7 +115,7 @@ __global__ void __launch_bounds__(TPB) k_init_records(const float *__restrict__ 
 
 // scales[0] = 2^kx applied to float products w*x, scales[1] = 2^km applied to w (both exact powers of two)
 __global__ void k_root_init(Node *nodes, NodeAcc *acc, int n, float3 lo, float3 hi, const unsigned *maxima,
-                            float *scales, LevelInfo *info) {
+                            float *scales, BuildState *st) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   Node r;
   r.count = n; r.offset = 0; r.cl = 0; r.cr = 0;
@@ -136,11 +135,13 @@ __global__ void k_root_init(Node *nodes, NodeAcc *acc, int n, float3 lo, float3 
   kx = max(-100, min(100, kx)); km = max(-100, min(100, km));
   scales[0] = ldexpf(1.0f, kx); scales[1] = ldexpf(1.0f, km);
   scales[2] = (float)(km - kx);   // exponent to undo: xc = (Sx / Sw) * 2^(km-kx)
-  info->begin = 0; info->end = 1; info->nsplit = 0; info->error = 0;
-  info->unit_mass = (n > 0 && maxima[2] == 0u) ? 1 : 0;
+  st->error = 0; st->tile_ticket = 0u; st->node_ticket = 0u;
+  st->unit_mass = (n > 0 && maxima[2] == 0u) ? 1 : 0;
+  for (int L = 0; L < 128; ++L) { st->nsplit[L] = -1; st->lvl_begin[L] = 0; st->lvl_end[L] = 0; }
+  st->lvl_begin[0] = 0; st->lvl_end[0] = 1; st->lvl_begin[128] = 0; st->lvl_end[128] = 0;
 }
 
-// ---- pass A: per-tile partial sums ---------------------------------------------------------------
+// ---- per-node partial sums ---------------------------------------------------------------------------
 struct Part {
   unsigned umin[3], umax[3];
   long long s[4];
@@ -149,16 +150,19 @@ __device__ __forceinline__ void part_reset(Part &p) {
   p.umin[0] = p.umin[1] = p.umin[2] = 0xffffffffu; p.umax[0] = p.umax[1] = p.umax[2] = 0u;
   p.s[0] = p.s[1] = p.s[2] = p.s[3] = 0;
 }
+// the product w*x is formed in float exactly as in BGQCM.c:203-206, then summed exactly (fixed point)
+__device__ __forceinline__ void part_add_sums(long long (&s)[4], const float4 &r, float sx, float sm) {
+  s[0] += __float2ll_rn(__fmul_rn(__fmul_rn(r.w, r.x), sx));
+  s[1] += __float2ll_rn(__fmul_rn(__fmul_rn(r.w, r.y), sx));
+  s[2] += __float2ll_rn(__fmul_rn(__fmul_rn(r.w, r.z), sx));
+  s[3] += __float2ll_rn(__fmul_rn(r.w, sm));
+}
 __device__ __forceinline__ void part_add(Part &p, const float4 &r, float sx, float sm) {
   unsigned ex = enc_f(r.x), ey = enc_f(r.y), ez = enc_f(r.z);
   p.umin[0] = min(p.umin[0], ex); p.umax[0] = max(p.umax[0], ex);
   p.umin[1] = min(p.umin[1], ey); p.umax[1] = max(p.umax[1], ey);
   p.umin[2] = min(p.umin[2], ez); p.umax[2] = max(p.umax[2], ez);
-  // the product w*x is formed in float exactly as in BGQCM.c:203-206, then summed exactly
-  p.s[0] += __float2ll_rn(__fmul_rn(__fmul_rn(r.w, r.x), sx));
-  p.s[1] += __float2ll_rn(__fmul_rn(__fmul_rn(r.w, r.y), sx));
-  p.s[2] += __float2ll_rn(__fmul_rn(__fmul_rn(r.w, r.z), sx));
-  p.s[3] += __float2ll_rn(__fmul_rn(r.w, sm));
+  part_add_sums(p.s, r, sx, sm);
 }
 
 struct Slot {
@@ -166,6 +170,10 @@ struct Slot {
   unsigned used, pad;
   unsigned long long s[4];
 };
+__device__ __forceinline__ void slot_reset(Slot &S) {
+  S.umin[0] = S.umin[1] = S.umin[2] = 0xffffffffu; S.umax[0] = S.umax[1] = S.umax[2] = 0u;
+  S.used = 0; S.s[0] = S.s[1] = S.s[2] = S.s[3] = 0;
+}
 
 __device__ __forceinline__ void flush_part(const Part &p, int nd, int n0, Slot *slots, NodeAcc *acc) {
   int sl = nd - n0;
@@ -181,16 +189,11 @@ __device__ __forceinline__ void flush_part(const Part &p, int nd, int n0, Slot *
   }
 }
 
+// Box and centroid sums of the ROOT (every deeper node gets them from the split pass that creates it).
 // A warp owns CM_IPT rows of 32 consecutive particles (coalesced 128-byte node-id and 512-byte record loads, CM_IPT of
-// each in flight per lane).  Node ids are non-decreasing along the array, so those 32*CM_IPT particles are one to three
-// runs; for each distinct node in turn (a warp-uniform loop) every lane sums its particles of that node, the 32 partials
-// are combined by a plain warp reduction -- REDUX for the six box bounds, a shuffle tree for the four 64-bit sums -- and
-// lane 0 adds the result to the block's shared-memory slot of the node.  (The first version striped items over the
-// block and fell back to per-thread shared atomics; the second combined per-thread partials of 4 consecutive
-// particles with a 14-word segmented warp scan -- 75 shuffles per 128 particles, issue-bound at 35 % of the HBM peak,
-// profiles/r1j_build_ncu_summary.md.)
-// (8 rows, no register cap: 4 rows or __launch_bounds__ minimum-block counts of 3-4 on any of the three tile kernels
-// spill and were 4-18 % slower on the whole build)
+// each in flight per lane); every lane sums its particles, the 32 partials are combined by a plain warp reduction --
+// REDUX for the six box bounds, a shuffle tree for the four 64-bit sums -- and lane 0 adds the result to the block's
+// shared-memory slot, flushed to the node's global accumulator once per block.
 static constexpr int CM_IPT = 8;
 static constexpr int CM_TILE = TPB * CM_IPT;
 
@@ -216,11 +219,7 @@ __global__ void __launch_bounds__(TPB) k_cm_tile(const float4 *__restrict__ rec,
 #pragma unroll
   for (int k = 0; k < CM_IPT; ++k) if (nd[k] >= 0) r[k] = __ldcs(rec + wbase + 32 * k);
   if (t == 0) s_n0 = INT_MAX;
-  if (t < SMAX) {
-    Slot &S = slots[t];
-    S.umin[0] = S.umin[1] = S.umin[2] = 0xffffffffu; S.umax[0] = S.umax[1] = S.umax[2] = 0u;
-    S.used = 0; S.s[0] = S.s[1] = S.s[2] = S.s[3] = 0;
-  }
+  if (t < SMAX) slot_reset(slots[t]);
   __syncthreads();
   int mn = INT_MAX;
 #pragma unroll
@@ -259,231 +258,501 @@ __global__ void __launch_bounds__(TPB) k_cm_tile(const float4 *__restrict__ rec,
   }
 }
 
-// Alternative k_cm_tile, selected with HACCSR_CM_KERNEL=warp (off by default: measured stand-alone only, see
-// tools/microbench_cm.cu and profiles/r1o_microbench_cm.txt -- identical accumulators, 6-25 % faster -- but the parity suite
-// has not been run on it inside the library yet).  Persistent warps over CONTIGUOUS particle ranges: the next rows' loads are
-// in flight during the current rows' arithmetic, the node's per-lane partial stays in registers while the node id stays the
-// same and is reduced and flushed with result-less global atomics only when the id changes; no shared memory, no barriers.
-static constexpr int CMW_ROWS = 4;
-__global__ void __launch_bounds__(TPB) k_cm_warp(const float4 *__restrict__ rec, const int *__restrict__ nid, int n,
-                                                 int per_warp, NodeAcc *__restrict__ acc, const float *__restrict__ scales) {
-  const int lane = threadIdx.x & 31;
-  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long b64 = gw * (long long)per_warp;
-  if (b64 >= n) return;
-  const int begin = (int)b64, end = (int)min((long long)n, b64 + per_warp);
-  const float sx = scales[0], sm = scales[1];
-  constexpr int STEP = 32 * CMW_ROWS;
-  int nd[CMW_ROWS], nd1[CMW_ROWS];
-  float4 r[CMW_ROWS], r1[CMW_ROWS];
-  auto load = [&](int pos, int (&d)[CMW_ROWS], float4 (&q)[CMW_ROWS]) {
+// ---- decoupled look-back (tile descriptors of the split pass, block descriptors of the node kernel) ---------------------
+// One 64-bit word per tile: epoch << 34 | status << 32 | value.  The epoch is level + 1, so a word left by an earlier level
+// (or the zero the build starts from) reads as "not published yet"; the value travels in the same word as the status, so a
+// plain 64-bit store / load pair needs no fence.
+static constexpr unsigned long long ST_AGG = 1ull, ST_PREFIX = 2ull;
+__device__ __forceinline__ unsigned long long desc_make(unsigned epoch, unsigned long long status, unsigned v) {
+  return ((unsigned long long)epoch << 34) | (status << 32) | (unsigned long long)v;
+}
+__device__ __forceinline__ void desc_store(unsigned long long *p, unsigned long long w) { *(volatile unsigned long long *)p = w; }
+__device__ __forceinline__ unsigned long long desc_load(const unsigned long long *p) { return *(const volatile unsigned long long *)p; }
+
+// Warp-collective: the sum of the values of descriptors pos, pos-1, ... down to and including the nearest inclusive prefix.
+// W windows of 32 descriptors are read at once (one L2 round trip for a look-back of 32*W tiles); a word that is not
+// published yet makes the warp read again from there.  Terminates because every tile with a smaller ticket is held by a
+// running block that publishes its aggregate before it waits for anything (tickets are handed out in increasing order).
+template <int W>
+__device__ __forceinline__ unsigned lookback(const unsigned long long *desc, int pos, unsigned epoch, int lane) {
+  unsigned sum = 0;
+  while (pos >= 0) {
+    unsigned long long d[W];
 #pragma unroll
-    for (int k = 0; k < CMW_ROWS; ++k) { const int i = pos + 32 * k + lane; d[k] = (i < end) ? __ldcs(nid + i) : -1; }
-#pragma unroll
-    for (int k = 0; k < CMW_ROWS; ++k) if (d[k] >= 0) q[k] = __ldcs(rec + pos + 32 * k + lane);
-  };
-  auto reduce_flush = [&](Part &p, int node) {
-#pragma unroll
-    for (int q = 0; q < 3; ++q) { p.umin[q] = __reduce_min_sync(0xffffffffu, p.umin[q]); p.umax[q] = __reduce_max_sync(0xffffffffu, p.umax[q]); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) p.s[q] += shfl_xor_ll(p.s[q], o);
+    for (int q = 0; q < W; ++q) {
+      const int j = pos - (q * 32 + lane);
+      d[q] = j >= 0 ? desc_load(desc + j) : desc_make(epoch, ST_PREFIX, 0u);
     }
-    if (lane == 0) {
-      NodeAcc &A = acc[node];
-      for (int k = 0; k < 3; ++k) { atomicMin(&A.umin[k], p.umin[k]); atomicMax(&A.umax[k], p.umax[k]); }
-      for (int k = 0; k < 4; ++k) add_split(&A.lo[k], &A.hi[k], p.s[k]);
-    }
-  };
-  load(begin, nd, r);
-  int K = -1;                 // node whose per-lane partial is carried in p
-  Part p; part_reset(p);
-  for (int pos = begin; pos < end; pos += STEP) {
-    load(pos + STEP, nd1, r1);         // rows past `end` load nothing
-    int mn = INT_MAX;
+    bool done = false;
+    int consumed = 0;
 #pragma unroll
-    for (int k = 0; k < CMW_ROWS; ++k) if (nd[k] >= 0) mn = min(mn, nd[k]);
-    int cur = __reduce_min_sync(0xffffffffu, mn);
-    while (cur != INT_MAX) {           // warp-uniform: the distinct nodes of this step, in increasing order
-      if (cur != K) {
-        if (K >= 0) reduce_flush(p, K);
-        part_reset(p); K = cur;
+    for (int q = 0; q < W; ++q) {
+      if (!done && consumed == q) {        // warp-uniform
+        const bool valid = (unsigned)(d[q] >> 34) == epoch;
+        const bool isp = valid && ((d[q] >> 32) & 3ull) == ST_PREFIX;
+        const unsigned bv = __ballot_sync(0xffffffffu, valid), bp = __ballot_sync(0xffffffffu, isp);
+        const unsigned lp = bp ? (unsigned)(__ffs(bp) - 1) : 31u;                 // nearest prefix of this window
+        const unsigned need = lp == 31u ? 0xffffffffu : ((2u << lp) - 1u);        // lanes 0 .. lp
+        if ((bv & need) == need) {
+          sum += __reduce_add_sync(0xffffffffu, ((need >> lane) & 1u) ? (unsigned)(d[q] & 0xffffffffull) : 0u);
+          consumed = q + 1;
+          done = bp != 0u;
+        }
       }
-      int next = INT_MAX;
-#pragma unroll
-      for (int k = 0; k < CMW_ROWS; ++k) {
-        if (nd[k] == cur) part_add(p, r[k], sx, sm);
-        else if (nd[k] > cur) next = min(next, nd[k]);
+    }
+    if (done) return sum;
+    pos -= 32 * consumed;
+  }
+  return sum;
+}
+
+__device__ __forceinline__ __int128 split_to_i128(unsigned long long lo, unsigned long long hi) {
+  return ((__int128)(long long)hi << 32) + (__int128)lo;
+}
+__device__ __forceinline__ double i128_to_double(__int128 t) {
+  // via the magnitude (avoids cancellation for small negative sums)
+  const bool neg = t < 0;
+  const unsigned __int128 m = neg ? (unsigned __int128)(-t) : (unsigned __int128)t;
+  const double d = (double)(unsigned long long)(m >> 64) * 18446744073709551616.0 + (double)(unsigned long long)m;
+  return neg ? -d : d;
+}
+
+// ---- node kernel: finalize the nodes of one level, decide splits, allocate children breadth-first --------------------------
+// One launch per level, no host round trip: the node range of the level was written by the previous level's launch into
+// BuildState, blocks take tickets (the host only knows an upper bound of the node count), and the rank of a split node among
+// the level's split nodes comes from a block scan plus a look-back over the blocks' counts, so children sit at
+// next_base + 2 * rank: the numbering is breadth-first and deterministic (parent index < child index, as the reference
+// guarantees at :808-809).
+// Sums: the split pass accumulates the centroid sums of LEFT children only; a right child's sums are its parent's minus its
+// sibling's -- exact, because they are integers.
+static constexpr int NTPB = 256;
+__global__ void __launch_bounds__(NTPB) k_level_nodes(Node *__restrict__ nodes, NodeAcc *__restrict__ acc,
+                                                      NodeTot *__restrict__ tot, BuildState *__restrict__ st,
+                                                      unsigned long long *__restrict__ ndesc, int level, int ppn,
+                                                      int max_nodes, const float *__restrict__ scales) {
+  __shared__ int s_w[34];
+  __shared__ int s_tk;
+  __shared__ unsigned s_base;
+  if (st->error || (level > 0 && st->nsplit[level - 1] <= 0)) return;     // the tree was finished by an earlier pass
+  const int begin = st->lvl_begin[level], end = st->lvl_end[level];
+  const int nblk = (end - begin + NTPB - 1) / NTPB;
+  if (threadIdx.x == 0) s_tk = (int)atomicAdd(&st->node_ticket, 1u);
+  __syncthreads();
+  const int tk = s_tk;
+  if (tk >= nblk) return;
+  const int k = begin + tk * NTPB + (int)threadIdx.x;
+  int split = 0;
+  if (k < end) {
+    Node nd = nodes[k];
+    int d = -1;
+    const int dir = nd.split == -2;        // the node's particles lie in reverse order (see k_split_pass)
+    if (level > 0) {
+      // a split that left one side empty (RCBForceTree.cxx:727-729): the parent stays an (oversized) leaf whose monopole is
+      // the sum over its empty children, i.e. zero (:856-889), and both children stay empty orphans.  The pass has labelled
+      // the parent's particles with one of the orphans; this level's pass writes them to their final place.
+      const int kl = begin + ((k - begin) & ~1);
+      const int c0 = nodes[kl].count, c1 = nodes[kl + 1].count;
+      if (c0 == 0 || c1 == 0) {
+        nd.count = 0;
+        if (k == kl) { Node *p = nodes + nd.parent; p->cl = 0; p->cr = 0; p->ppm = 0.f; }
       }
-      cur = __reduce_min_sync(0xffffffffu, next);
     }
+    if (nd.count > 0) {
+      const NodeAcc a = acc[k];
+      __int128 T[4];
+      if (level == 0 || ((k - begin) & 1) == 0) {
 #pragma unroll
-    for (int k = 0; k < CMW_ROWS; ++k) { nd[k] = nd1[k]; r[k] = r1[k]; }
-  }
-  if (K >= 0) reduce_flush(p, K);
-}
-
-// ---- pass B: finalize the nodes of one level, decide splits, allocate children breadth-first ----------
-// Three launches so that a level of 65 k nodes is as parallel as a level of one: (a) per node: box, centroid, split
-// decision; (b) k_scan over the split flags; (c) per split node: children at next_base + 2 * rank, so the numbering is
-// breadth-first and deterministic (parent index < child index, as the reference guarantees at :808-809).
-__global__ void __launch_bounds__(256) k_level_decide(Node *__restrict__ nodes, const NodeAcc *__restrict__ acc,
-                                                       int begin, int end, int ppn, const float *__restrict__ scales,
-                                                       unsigned *__restrict__ flags, LevelInfo *__restrict__ info) {
-  const int k = begin + blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == begin) info->error = 0;
-  if (k >= end) return;
-  const double undo = ldexp(1.0, (int)scales[2]);
-  Node nd = nodes[k];
-  int split = 0, d = -1;
-  if (nd.count > 0) {
-    const NodeAcc a = acc[k];
-    for (int q = 0; q < 3; ++q) { nd.xmin[q] = dec_f(a.umin[q]); nd.xmax[q] = dec_f(a.umax[q]); }
-    const double sw = split_to_double(a.lo[3], a.hi[3]);
-    for (int q = 0; q < 3; ++q) {
-      const double sxq = split_to_double(a.lo[q], a.hi[q]);
-      nd.xc[q] = (float)((sxq / sw) * undo);                       // BGQCM.c:209-211
+        for (int q = 0; q < 4; ++q) T[q] = split_to_i128(a.lo[q], a.hi[q]);
+      } else {
+        const NodeTot pt = tot[nd.parent];
+        const NodeAcc sib = acc[k - 1];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          T[q] = (((__int128)(long long)pt.hi[q] << 64) | (__int128)pt.lo[q]) - split_to_i128(sib.lo[q], sib.hi[q]);
+      }
+      NodeTot o;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { o.lo[q] = (unsigned long long)T[q]; o.hi[q] = (unsigned long long)(T[q] >> 64); }
+      tot[k] = o;
+      const double undo = ldexp(1.0, (int)scales[2]);
+      for (int q = 0; q < 3; ++q) { nd.xmin[q] = dec_f(a.umin[q]); nd.xmax[q] = dec_f(a.umax[q]); }
+      const double sw = i128_to_double(T[3]);
+      for (int q = 0; q < 3; ++q) nd.xc[q] = (float)((i128_to_double(T[q]) / sw) * undo);     // BGQCM.c:209-211
+      if (nd.count > ppn) {                                          // RCBForceTree.cxx:788
+        const float l0 = __fsub_rn(nd.xmax[0], nd.xmin[0]), l1 = __fsub_rn(nd.xmax[1], nd.xmin[1]),
+                    l2 = __fsub_rn(nd.xmax[2], nd.xmin[2]);
+        d = (l0 > l1 && l0 > l2) ? 0 : ((l1 > l2) ? 1 : 2);          // :844-852
+        split = 1;
+      } else {
+        // leaf monopole: sum of masses (pp<1>, :536-569); unused when count <= 1 (:788-797)
+        nd.ppm = (nd.count > 1) ? (float)(sw / (double)scales[1]) : 0.f;
+      }
     }
-    if (nd.count > ppn) {                                          // RCBForceTree.cxx:788
-      const float l0 = __fsub_rn(nd.xmax[0], nd.xmin[0]), l1 = __fsub_rn(nd.xmax[1], nd.xmin[1]),
-                  l2 = __fsub_rn(nd.xmax[2], nd.xmin[2]);
-      d = (l0 > l1 && l0 > l2) ? 0 : ((l1 > l2) ? 1 : 2);          // :844-852
-      split = 1;
-    } else {
-      // leaf monopole: sum of masses (pp<1>, :536-569); unused when count <= 1 (:788-797)
-      nd.ppm = (nd.count > 1) ? (float)(sw / (double)scales[1]) : 0.f;
+    nd.split = split ? (d | (dir << 2)) : (dir ? -2 : -1);
+    nodes[k] = nd;
+  }
+  int total;
+  const int excl = block_excl_scan(split, s_w, &total);
+  const unsigned epoch = (unsigned)level + 1u;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    if (lane == 0) desc_store(ndesc + tk, desc_make(epoch, tk == 0 ? ST_PREFIX : ST_AGG, (unsigned)total));
+    unsigned base = 0;
+    if (tk > 0) {
+      base = lookback<1>(ndesc, tk - 1, epoch, lane);
+      if (lane == 0) desc_store(ndesc + tk, desc_make(epoch, ST_PREFIX, base + (unsigned)total));
+    }
+    if (lane == 0) s_base = base;
+  }
+  __syncthreads();
+  const int next_base = end;
+  if (split) {
+    const int cl = next_base + 2 * ((int)s_base + excl);
+    if (cl + 1 < max_nodes) {
+      Node nd = nodes[k];
+      const int d = nd.split & 3, dir = (nd.split >> 2) & 1;
+      nodes[k].cl = cl; nodes[k].cr = cl + 1;     // withdrawn by the next level's launch on a degenerate split
+      Node c;
+      c.count = 0; c.offset = 0; c.cl = 0; c.cr = 0; c.ppm = 0.f; c.parent = k; c.split = -1;
+      for (int q = 0; q < 3; ++q) { c.xmin[q] = nd.xmin[q]; c.xmax[q] = nd.xmax[q]; c.xc[q] = 0.f; }
+      Node l = c, r = c;
+      l.xmax[d] = nd.xc[d]; r.xmin[d] = nd.xc[d];                  // :747,763
+      l.split = dir ? -2 : -1; r.split = dir ? -1 : -2;            // a left child keeps its parent's direction, a right child reverses it
+      nodes[cl] = l; nodes[cl + 1] = r;
+      NodeAcc z;
+      for (int q = 0; q < 3; ++q) { z.umin[q] = 0xffffffffu; z.umax[q] = 0u; }
+      for (int q = 0; q < 4; ++q) { z.lo[q] = 0; z.hi[q] = 0; }
+      acc[cl] = z; acc[cl + 1] = z;
     }
   }
-  nd.split = split ? d : -1;
-  nodes[k] = nd;
-  flags[k - begin] = (unsigned)split;
-}
-
-__global__ void __launch_bounds__(256) k_level_children(Node *__restrict__ nodes, NodeAcc *__restrict__ acc, int begin,
-                                                         int end, int next_base, int max_nodes,
-                                                         const unsigned *__restrict__ flags,
-                                                         const unsigned *__restrict__ ranks,
-                                                         const unsigned long long *__restrict__ d_total,
-                                                         LevelInfo *__restrict__ info) {
-  const int k = begin + blockIdx.x * blockDim.x + threadIdx.x;
-  const int ns = (int)*d_total;
-  const bool overflow = next_base + 2 * ns >= max_nodes;      // the last child index must stay below max_nodes
-  if (k == begin) {
-    info->begin = next_base; info->end = next_base + (overflow ? 0 : 2 * ns); info->nsplit = overflow ? 0 : ns;
-    info->error = overflow ? 1 : 0;
-  }
-  if (k >= end || !flags[k - begin]) return;
-  if (overflow) { nodes[k].split = -1; return; }
-  Node nd = nodes[k];
-  const int d = nd.split;
-  const int cl = next_base + 2 * (int)ranks[k - begin];
-  nodes[k].cl = cl; nodes[k].cr = cl + 1;     // provisional; cleared by k_set_children on a degenerate split
-  Node c;
-  c.count = 0; c.offset = 0; c.cl = 0; c.cr = 0; c.ppm = 0.f; c.parent = k; c.split = -1;
-  for (int q = 0; q < 3; ++q) { c.xmin[q] = nd.xmin[q]; c.xmax[q] = nd.xmax[q]; c.xc[q] = 0.f; }
-  Node l = c, r = c;
-  l.xmax[d] = nd.xc[d]; r.xmin[d] = nd.xc[d];                  // :747,763
-  nodes[cl] = l; nodes[cl + 1] = r;
-  NodeAcc z;
-  for (int q = 0; q < 3; ++q) { z.umin[q] = 0xffffffffu; z.umax[q] = 0u; }
-  for (int q = 0; q < 4; ++q) { z.lo[q] = 0; z.hi[q] = 0; }
-  acc[cl] = z; acc[cl + 1] = z;
-}
-
-// ---- shared by C1 and C3: left flags of a tile and their exclusive prefix in particle order --------------
-struct ItemInfo { int sp, flag, excl, offset, count, cl, cr; };
-
-// striped tile layout of the flag passes: particle i = tile*TILE + j*TPB + t
-__device__ __forceinline__ void st_load_nid(const int *__restrict__ nid, int n, int tile, int ntiles, int nd[IPT]) {
-#pragma unroll
-  for (int j = 0; j < IPT; ++j) {
-    const int i = tile * TILE + j * TPB + (int)threadIdx.x;
-    nd[j] = (tile < ntiles && i < n) ? __ldcs(nid + i) : -1;
+  if (tk == nblk - 1 && threadIdx.x == 0) {
+    const int ns = (int)s_base + total;
+    const bool overflow = next_base + 2 * ns >= max_nodes;      // the last child index must stay below max_nodes
+    st->lvl_begin[level + 1] = next_base;
+    st->lvl_end[level + 1] = next_base + (overflow ? 0 : 2 * ns);
+    st->nsplit[level] = overflow ? 0 : ns;
+    if (overflow) st->error = 1;
+    st->tile_ticket = 0u;
   }
 }
-__device__ __forceinline__ void st_load_rec(const float4 *__restrict__ rec, int tile, const int nd[IPT], float4 r[IPT]) {
-#pragma unroll
-  for (int j = 0; j < IPT; ++j) if (nd[j] >= 0) r[j] = __ldcs(rec + tile * TILE + j * TPB + (int)threadIdx.x);
+
+// ---- the split pass: one streaming pass over the particles per tree level -----------------------------------------------------
+// Reads every record once and writes it once.  For a particle of a node that splits at this level: left flag from the pivot
+// (key < centroid coordinate, :640), its rank among the node's left (right) particles before it, destination in the other
+// record buffer, and its contribution to the box and centroid sums of the child it moves to, so the children need no pass
+// of their own.  Particles of nodes that became leaves are written to their final place in src4 / perm.
+// Left particles fill the node's range from the front, right particles from the back, so no particle needs the node's total
+// left count (which only the node's last tile knows).  That writes the right block in reverse; a node therefore carries a
+// direction (Node::split bit 2, or -2 for a leaf): scanning a reversed node front to back meets its particles last to
+// first, so its left block comes out reversed and its right block in order -- a child's direction is its parent's, flipped
+// for right children -- and a reversed leaf is mirrored when it is written to its final place.  The result is the STABLE
+// partition on both sides: the order inside every leaf is a fixed function of the input order, and building the tree
+// again from its own output leaves every particle where it is (like the reference's swap loop, :648-669).
+//
+// The rank needs the number of left particles of the node in all earlier tiles.  Tiles are taken in ticket order; each
+// publishes the left count of its LAST node segment (the lefts behind its last node start) as an aggregate, or as an
+// inclusive prefix when that segment starts inside the tile, and a tile whose first node started earlier sums its
+// predecessors' words back to the nearest prefix (decoupled look-back, one L2 round trip for 32*LB_W tiles).  Inside the
+// tile a segmented scan over the 32 per-(row, warp) ballots gives every particle the lefts since the last node start.
+static constexpr int NSLOT = 32;       // children of one tile accumulated in shared memory (more: straight to global)
+static constexpr int LB_W = 8;         // look-back windows read at once
+static constexpr int NST = 4;          // tiles of the shared-memory ring: B stage, A stage, two in flight
+static constexpr int SLOT_REC = 0, SLOT_IDX = TILE * 16, SLOT_NID = TILE * 20, SLOT_BYTES = TILE * 24;
+
+__device__ __forceinline__ unsigned tb_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tb_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void st_load_idx(const unsigned *__restrict__ idx, int tile, const int nd[IPT], unsigned x[IPT]) {
-#pragma unroll
-  for (int j = 0; j < IPT; ++j) if (nd[j] >= 0) x[j] = __ldcs(idx + tile * TILE + j * TPB + (int)threadIdx.x);
+__device__ __forceinline__ void tb_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tb_mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tb_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ int tile_flags_scan(const Node *__restrict__ nodes, const int nd[IPT], const float4 r[IPT],
-                                               ItemInfo it[IPT], int *s_w) {
-  // In particle order the tile is IPT rows of TPB/32 warps.  One ballot per (row, warp) gives the left count of 32
-  // consecutive particles; the IPT*TPB/32 = 32 counts are scanned by one warp -- a single barrier pair instead of IPT
-  // block-wide scans.  The node's metadata comes in three independent 16-byte loads (no load depends on the split
-  // dimension read by another).
-  static_assert(IPT * (TPB / 32) == 32, "one warp scans the per-(row, warp) counts");
+// exact warp sum of per-lane 64-bit partials |v| < 2^57 as three REDUX.SUM over 21-bit limbs
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+  const int l0 = (int)(v & 0x1fffffll), l1 = (int)((v >> 21) & 0x1fffffll), l2 = (int)(v >> 42);
+  const int s0 = __reduce_add_sync(0xffffffffu, l0), s1 = __reduce_add_sync(0xffffffffu, l1), s2 = __reduce_add_sync(0xffffffffu, l2);
+  return (long long)s0 + ((long long)s1 << 21) + ((long long)s2 << 42);
+}
+
+// Structure of the kernel.  Tiles go round the blocks (block b owns tiles b, b+G, b+2G, ...: in iteration k the grid works
+// on G consecutive tiles) and travel through a ring of NST shared-memory slots filled by 1-D TMA bulk copies (records, indices
+// and node ids of a tile are three contiguous ranges; one thread posts them three tiles ahead, nobody stages anything in
+// registers).  A tile is visited twice, one iteration apart:
+//   A stage (tile k+1): left flags and node starts -> ballots, the segmented scan, and the tile's look-back word is PUBLISHED;
+//   B stage (tile k)  : look-back (every word it meets was published an iteration ago, so it reads, it does not wait),
+//                       destinations, stores, children's sums.
+// Publishing a tile's count in the same iteration that consumes its predecessors' counts makes all blocks march in step
+// and leaves the warps waiting at the barrier behind the look-back (measured: 54 % of all stall samples, 0.7 ms per
+// level); with the count one iteration ahead a block can run an iteration ahead of its neighbours.
+__global__ void __launch_bounds__(TPB, 2) k_split_pass(const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
+                                                       const int *__restrict__ nid, Node *__restrict__ nodes,
+                                                       NodeAcc *__restrict__ acc, const float *__restrict__ scales,
+                                                       BuildState *__restrict__ st, unsigned long long *__restrict__ desc,
+                                                       int level, int n, int ntiles, float4 *__restrict__ rec_out,
+                                                       unsigned *__restrict__ idx_out, int *__restrict__ nid_out,
+                                                       float4 *__restrict__ src4, unsigned *__restrict__ perm) {
+  static_assert(IPT * (TPB / 32) == 32, "one warp scans the per-(row, warp) entries");
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ unsigned s_fb[NST][32], s_hb[NST][32];   // per slot and (row, warp) entry: ballots of the left flags and of the node starts
+  __shared__ int s_cv[NST][32], s_cf[NST][32];        // per slot: exclusive segmented scan of the entries
+  __shared__ int s_ev[32], s_ef[32];                  // A stage: lefts behind the entry's last node start (or all of them), has a node start
+  __shared__ int s_misc[NST][4];   // per slot: [0] first node started in an earlier tile, [1] smallest child id, [2] carry, [3] own word
+  __shared__ unsigned long long s_bar[NST];
+  __shared__ Slot slots[NSLOT];
+  if (st->error || (level > 0 && st->nsplit[level - 1] <= 0)) return;     // the tree was finished by an earlier pass
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  unsigned bal[IPT];
-#pragma unroll
-  for (int j = 0; j < IPT; ++j) {
-    int sp = -1, flag = 0;
-    it[j].offset = 0; it[j].count = 0; it[j].cl = 0; it[j].cr = 0;
-    if (nd[j] >= 0) {
-      const float4 *np = reinterpret_cast<const float4 *>(nodes + nd[j]);
-      const float4 a = __ldg(np), c = __ldg(np + 2), d = __ldg(np + 3);
-      sp = __float_as_int(d.w);
-      it[j].count = __float_as_int(a.x); it[j].offset = __float_as_int(a.y);
-      it[j].cl = __float_as_int(a.z); it[j].cr = __float_as_int(a.w);
-      if (sp >= 0) {
-        const float pivot = sp == 0 ? c.z : (sp == 1 ? c.w : d.x);             // xc[sp], RCBForceTree.cxx:720
-        flag = comp(r[j], sp) < pivot;                                         // :640
-      }
-    }
-    bal[j] = __ballot_sync(0xffffffffu, flag);
-    it[j].sp = sp; it[j].flag = flag;
-    if (lane == 0) s_w[j * (TPB / 32) + w] = __popc(bal[j]);
+  const unsigned epoch = (unsigned)level + 1u;
+  const unsigned below = (1u << lane) - 1u;
+  const float sx = scales[0], sm = scales[1];
+  const int G = gridDim.x, T00 = blockIdx.x;
+  if (t == 0) {
+    if (blockIdx.x == 0) st->node_ticket = 0u;
+    for (int q = 0; q < NST; ++q) { tb_mbar_init(tb_smem_u32(&s_bar[q]), 1); s_misc[q][0] = 0; s_misc[q][1] = INT_MAX; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (t < NSLOT) slot_reset(slots[t]);
   __syncthreads();
-  if (w == 0) {
-    int x = s_w[lane], inc = x;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += y;
-    }
-    s_w[lane] = inc - x;
-    if (lane == 31) s_w[32] = inc;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < IPT; ++j) it[j].excl = s_w[j * (TPB / 32) + w] + __popc(bal[j] & ((1u << lane) - 1u));
-  return s_w[32];
-}
-
-__global__ void __launch_bounds__(TPB) k_left_count(const float4 *__restrict__ rec, const int *__restrict__ nid,
-                                                    const Node *__restrict__ nodes, int n, int ntiles,
-                                                    unsigned *__restrict__ tilecount, int *__restrict__ lstart,
-                                                    int *__restrict__ lend) {
-  __shared__ int s_w[2][34];     // alternating per iteration: a slow warp may still read the previous tile's prefixes
-  const int stride = gridDim.x;
-  int nd[IPT], nd1[IPT], nd2[IPT];
-  float4 r[IPT], r1[IPT];
-  ItemInfo it[IPT];
-  int tile = blockIdx.x;
-  st_load_nid(nid, n, tile, ntiles, nd);
-  st_load_nid(nid, n, tile + stride, ntiles, nd1);
-  st_load_rec(rec, tile, nd, r);
-  for (int k = 0; tile < ntiles; tile += stride, ++k) {
-    st_load_nid(nid, n, tile + 2 * stride, ntiles, nd2);
-    st_load_rec(rec, tile + stride, nd1, r1);
-    const int total = tile_flags_scan(nodes, nd, r, it, s_w[k & 1]);
+  // one thread posts the three bulk copies of tile number k of this block
+  auto issue = [&](int k) {
+    const int T = T00 + k * G;
+    if (T >= ntiles) return;
+    const int q = k % NST, i0 = T * TILE;
+    const int cnt = min(TILE, n - i0);
+    const unsigned b4 = (unsigned)(((cnt * 4) + 15) & ~15);
+    const unsigned bar = tb_smem_u32(&s_bar[q]), base = tb_smem_u32(ring + (size_t)q * SLOT_BYTES);
+    s_misc[q][0] = 0; s_misc[q][1] = INT_MAX;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tb_mbar_expect_tx(bar, (unsigned)cnt * 16u + 2u * b4);
+    tb_bulk_g2s(base + SLOT_REC, rec + i0, (unsigned)cnt * 16u, bar);
+    tb_bulk_g2s(base + SLOT_IDX, idx + i0, b4, bar);
+    tb_bulk_g2s(base + SLOT_NID, nid + i0, b4, bar);
+  };
+  // A stage of tile number k: flags, node starts, ballots, entries (consumed by warp 0 behind the next barrier)
+  auto stage_a = [&](int k) {
+    const int T = T00 + k * G, q = k % NST, tile0 = T * TILE;
+    tb_mbar_wait(tb_smem_u32(&s_bar[q]), (unsigned)((k / NST) & 1));
+    const unsigned char *sl = ring + (size_t)q * SLOT_BYTES;
+    const int *nidS = reinterpret_cast<const int *>(sl + SLOT_NID);
+    const float *recS = reinterpret_cast<const float *>(sl + SLOT_REC);
+    int cmin = INT_MAX;
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
-      if (it[j].sp >= 0) {
-        const int i = tile * TILE + j * TPB + (int)threadIdx.x;
-        if (i == it[j].offset) lstart[nd[j]] = it[j].excl;
-        if (i == it[j].offset + it[j].count - 1) lend[nd[j]] = it[j].excl + it[j].flag;
+      const int p = j * TPB + t, i = tile0 + p;
+      int flag = 0, head = 0;
+      const int ndv = i < n ? nidS[p] : -1;
+      if (ndv >= 0) {
+        const float4 *np = reinterpret_cast<const float4 *>(nodes + ndv);
+        const float4 a = __ldg(np);
+        const int cl = __float_as_int(a.z);
+        if (cl > 0) {                                                            // the node splits at this level
+          const float4 c = __ldg(np + 2), d = __ldg(np + 3);
+          const int sp = __float_as_int(d.w) & 3, off = __float_as_int(a.y);
+          const float pivot = sp == 0 ? c.z : (sp == 1 ? c.w : d.x);             // xc[sp], RCBForceTree.cxx:720
+          flag = recS[4 * p + sp] < pivot;                                       // :640
+          head = i == off;
+          cmin = min(cmin, cl);
+          if (p == 0 && off < tile0) s_misc[q][0] = 1;
+        }
+      }
+      const unsigned fb = __ballot_sync(0xffffffffu, flag), hb = __ballot_sync(0xffffffffu, head);
+      if (lane == 0) {
+        const int e = j * (TPB / 32) + w;
+        s_fb[q][e] = fb; s_hb[q][e] = hb;
+        s_ev[e] = hb ? __popc(fb >> (31 - __clz(hb))) : __popc(fb);
+        s_ef[e] = hb != 0u;
       }
     }
-    if (threadIdx.x == 0) tilecount[tile] = (unsigned)total;
+    cmin = __reduce_min_sync(0xffffffffu, cmin);
+    if (lane == 0 && cmin != INT_MAX) atomicMin(&s_misc[q][1], cmin);
+  };
+  // warp 0, behind the barrier that follows stage_a: segmented scan of the entries, publish the tile's word
+  auto scan_publish = [&](int k) {
+    const int T = T00 + k * G, q = k % NST;
+    int iv = s_ev[lane], iff = s_ef[lane];
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) { nd[j] = nd1[j]; nd1[j] = nd2[j]; r[j] = r1[j]; }
+    for (int o = 1; o < 32; o <<= 1) {
+      const int pv = __shfl_up_sync(0xffffffffu, iv, o), pf = __shfl_up_sync(0xffffffffu, iff, o);
+      if (lane >= o) { if (!iff) iv += pv; iff |= pf; }
+    }
+    int ev = __shfl_up_sync(0xffffffffu, iv, 1), ef = __shfl_up_sync(0xffffffffu, iff, 1);
+    if (lane == 0) { ev = 0; ef = 0; }
+    s_cv[q][lane] = ev; s_cf[q][lane] = ef;
+    if (lane == 31) {
+      const int need = s_misc[q][0];
+      desc_store(desc + T, desc_make(epoch, (!need || iff) ? ST_PREFIX : ST_AGG, (unsigned)iv));
+      s_misc[q][3] = iv | (iff << 31);
+    }
+  };
+  const int nk = T00 < ntiles ? (ntiles - T00 + G - 1) / G : 0;     // tiles of this block
+  if (t == 0) for (int k = 0; k < NST - 1; ++k) issue(k);
+  if (nk > 0) stage_a(0);
+  __syncthreads();
+  if (w == 0 && nk > 0) scan_publish(0);
+  __syncthreads();
+  for (int k = 0; k < nk; ++k) {
+    const int T0 = T00 + k * G, q = k % NST, tile0 = T0 * TILE;
+    if (t == 0) issue(k + NST - 1);           // its slot was tile k-1's: every thread left it before the last barrier
+    if (k + 1 < nk) stage_a(k + 1);
+    __syncthreads();
+    if (w == 0) {
+      if (k + 1 < nk) scan_publish(k + 1);
+      unsigned carry = 0;
+      if (s_misc[q][0]) {
+        carry = lookback<LB_W>(desc, T0 - 1, epoch, lane);
+        const int own = s_misc[q][3];
+        if (own >= 0 && lane == 0) desc_store(desc + T0, desc_make(epoch, ST_PREFIX, carry + (unsigned)own));
+      }
+      if (lane == 0) s_misc[q][2] = (int)carry;
+    }
+    __syncthreads();
+    // ---- B stage: destinations and stores ----------------------------------------------------------------------------------
+    const int carry = s_misc[q][2], cbase = s_misc[q][1];
+    const unsigned char *sl = ring + (size_t)q * SLOT_BYTES;
+    const int *nidS = reinterpret_cast<const int *>(sl + SLOT_NID);
+    const float4 *recS = reinterpret_cast<const float4 *>(sl + SLOT_REC);
+    const unsigned *idxS = reinterpret_cast<const unsigned *>(sl + SLOT_IDX);
+    float4 r[IPT];
+    int cl[IPT];             // > 0: child the particle's node sends its left particles to; else not a particle of a splitting node
+    unsigned fl = 0;         // bit j: left flag of item j
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      const int p = j * TPB + t, i = tile0 + p;
+      cl[j] = 0;
+      if (i >= n) continue;
+      const int ndv = nidS[p];
+      if (ndv < 0) { nid_out[i] = -1; continue; }
+      const float4 *np = reinterpret_cast<const float4 *>(nodes + ndv);
+      const float4 a = __ldg(np);
+      int cnt = __float_as_int(a.x), off = __float_as_int(a.y);
+      cl[j] = __float_as_int(a.z);
+      r[j] = recS[p];
+      const unsigned ix = idxS[p];
+      if (cl[j] <= 0) {                      // the node is a leaf (or an orphan holding a degenerate node's particles): final place
+        const float4 d = __ldg(np + 3);
+        int fin = i;
+        if (__float_as_int(d.w) == -2) {     // reversed: mirror the leaf (an orphan has its parent's range)
+          if (cnt == 0) {
+            const float4 pa = __ldg(reinterpret_cast<const float4 *>(nodes + __float_as_int(d.z)));
+            cnt = __float_as_int(pa.x); off = __float_as_int(pa.y);
+          }
+          fin = 2 * off + cnt - 1 - i;
+        }
+        src4[fin] = r[j]; perm[fin] = ix; nid_out[i] = -1;
+        continue;
+      }
+      const int e = j * (TPB / 32) + w;
+      const unsigned fb = s_fb[q][e], hb = s_hb[q][e];
+      const unsigned hm = hb & (below | (1u << lane));      // node starts at or before this lane in its row
+      int lb;
+      if (hm) {
+        lb = __popc(fb & below & ~((1u << (31 - __clz(hm))) - 1u));
+      } else {
+        lb = s_cv[q][e] + __popc(fb & below);
+        if (!s_cf[q][e]) lb += carry;                         // the node started in an earlier tile
+      }
+      const int flag = (fb >> lane) & 1u;
+      fl |= (unsigned)flag << j;
+      int dest, child;
+      if (flag) { dest = off + lb; child = cl[j]; }
+      else { dest = off + cnt - 1 - ((i - off) - lb); child = cl[j] + 1; }
+      rec_out[dest] = r[j]; idx_out[dest] = ix; nid_out[dest] = child;
+      if (i == off + cnt - 1) {                               // the node's last particle knows the split
+        const int is = lb + flag;
+        nodes[cl[j]].count = is;            nodes[cl[j]].offset = off;              // :731-746
+        nodes[cl[j] + 1].count = cnt - is;  nodes[cl[j] + 1].offset = off + is;     // :732,762
+      }
+    }
+    // ---- box and centroid sums of the children (warp-uniform loop over the distinct nodes of the warp's four rows) -----
+    {
+      int mk = INT_MAX;
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) if (cl[j] > 0) mk = min(mk, cl[j]);
+      int key = __reduce_min_sync(0xffffffffu, mk);
+      while (key != INT_MAX) {
+        unsigned bl[6], br[6];
+#pragma unroll
+        for (int qq = 0; qq < 3; ++qq) { bl[qq] = 0xffffffffu; bl[3 + qq] = 0u; br[qq] = 0xffffffffu; br[3 + qq] = 0u; }
+        long long s[4] = {0, 0, 0, 0};
+        int next = INT_MAX;
+        bool anyl = false, anyr = false;
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+          if (cl[j] == key) {
+            const unsigned ex = enc_f(r[j].x), ey = enc_f(r[j].y), ez = enc_f(r[j].z);
+            if ((fl >> j) & 1u) {
+              bl[0] = min(bl[0], ex); bl[1] = min(bl[1], ey); bl[2] = min(bl[2], ez);
+              bl[3] = max(bl[3], ex); bl[4] = max(bl[4], ey); bl[5] = max(bl[5], ez);
+              part_add_sums(s, r[j], sx, sm);
+              anyl = true;
+            } else {
+              br[0] = min(br[0], ex); br[1] = min(br[1], ey); br[2] = min(br[2], ez);
+              br[3] = max(br[3], ex); br[4] = max(br[4], ey); br[5] = max(br[5], ez);
+              anyr = true;
+            }
+          } else if (cl[j] > key) next = min(next, cl[j]);
+        }
+        const bool wl = __any_sync(0xffffffffu, anyl), wr = __any_sync(0xffffffffu, anyr);
+        if (wl) {
+#pragma unroll
+          for (int qq = 0; qq < 3; ++qq) { bl[qq] = __reduce_min_sync(0xffffffffu, bl[qq]); bl[3 + qq] = __reduce_max_sync(0xffffffffu, bl[3 + qq]); }
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) s[qq] = warp_sum_ll(s[qq]);
+        }
+        if (wr) {
+#pragma unroll
+          for (int qq = 0; qq < 3; ++qq) { br[qq] = __reduce_min_sync(0xffffffffu, br[qq]); br[3 + qq] = __reduce_max_sync(0xffffffffu, br[3 + qq]); }
+        }
+        if (lane == 0) {
+          const int sl2 = key - cbase;
+          if (sl2 >= 0 && sl2 + 1 < NSLOT) {
+            if (wl) {
+              Slot &S = slots[sl2];
+              for (int qq = 0; qq < 3; ++qq) { atomicMin(&S.umin[qq], bl[qq]); atomicMax(&S.umax[qq], bl[3 + qq]); }
+              for (int qq = 0; qq < 4; ++qq) atomicAdd(&S.s[qq], (unsigned long long)s[qq]);
+              S.used = 1;
+            }
+            if (wr) {
+              Slot &S = slots[sl2 + 1];
+              for (int qq = 0; qq < 3; ++qq) { atomicMin(&S.umin[qq], br[qq]); atomicMax(&S.umax[qq], br[3 + qq]); }
+              S.used = 1;
+            }
+          } else {
+            if (wl) {
+              NodeAcc &A = acc[key];
+              for (int qq = 0; qq < 3; ++qq) { atomicMin(&A.umin[qq], bl[qq]); atomicMax(&A.umax[qq], bl[3 + qq]); }
+              for (int qq = 0; qq < 4; ++qq) add_split(&A.lo[qq], &A.hi[qq], s[qq]);
+            }
+            if (wr) {
+              NodeAcc &A = acc[key + 1];
+              for (int qq = 0; qq < 3; ++qq) { atomicMin(&A.umin[qq], br[qq]); atomicMax(&A.umax[qq], br[3 + qq]); }
+            }
+          }
+        }
+        key = __reduce_min_sync(0xffffffffu, next);
+      }
+    }
+    __syncthreads();
+    if (t < NSLOT && slots[t].used) {
+      NodeAcc &A = acc[cbase + t];
+      Slot &S = slots[t];
+      for (int qq = 0; qq < 3; ++qq) { atomicMin(&A.umin[qq], S.umin[qq]); atomicMax(&A.umax[qq], S.umax[qq]); }
+      for (int qq = 0; qq < 4; ++qq) add_split(&A.lo[qq], &A.hi[qq], (long long)S.s[qq]);
+      slot_reset(S);
+    }
   }
 }
 
@@ -509,81 +778,6 @@ __global__ void __launch_bounds__(1024) k_scan(const unsigned *__restrict__ in, 
     running += (unsigned long long)(unsigned)total;
   }
   if (threadIdx.x == 0 && d_total) *d_total = running;
-}
-
-__global__ void k_set_children(Node *__restrict__ nodes, int begin, int end, const unsigned *__restrict__ tilebase,
-                               const int *__restrict__ lstart, const int *__restrict__ lend,
-                               int *__restrict__ lbase, int *__restrict__ nleft) {
-  int k = begin + blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= end) return;
-  Node nd = nodes[k];
-  if (nd.split < 0) return;
-  int ts = nd.offset / TILE, te = (nd.offset + nd.count - 1) / TILE;
-  int Ls = (int)tilebase[ts] + lstart[k], Le = (int)tilebase[te] + lend[k];
-  int is = Le - Ls;
-  if (is == 0 || is == nd.count) {
-    // degenerate split (RCBForceTree.cxx:727-729): the node stays a leaf, its two children stay empty
-    // orphans, and its monopole mass is the sum over those empty children, i.e. zero (:856-889).
-    // nodes[k].split keeps the dimension for the rest of this level so that k_scatter recomputes the
-    // same left flags k_left_count counted; nleft = -1 marks the node as finished.
-    nodes[k].cl = 0; nodes[k].cr = 0; nodes[k].ppm = 0.f; nleft[k] = -1;
-    return;
-  }
-  lbase[k] = Ls; nleft[k] = is;
-  nodes[nd.cl].count = is;            nodes[nd.cl].offset = nd.offset;         // :731-746
-  nodes[nd.cr].count = nd.count - is; nodes[nd.cr].offset = nd.offset + is;    // :732,762
-}
-
-__global__ void __launch_bounds__(TPB) k_scatter(const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
-                                                 const int *__restrict__ nid, const Node *__restrict__ nodes, int n,
-                                                 int ntiles, const unsigned *__restrict__ tilebase,
-                                                 const int *__restrict__ lbase, const int *__restrict__ nleft,
-                                                 float4 *__restrict__ rec_out, unsigned *__restrict__ idx_out,
-                                                 int *__restrict__ nid_out, float4 *__restrict__ src4,
-                                                 unsigned *__restrict__ perm) {
-  __shared__ int s_w[2][34];
-  const int stride = gridDim.x;
-  int nd[IPT], nd1[IPT], nd2[IPT];
-  float4 r[IPT], r1[IPT];
-  unsigned ix[IPT], ix1[IPT];
-  ItemInfo it[IPT];
-  int tile = blockIdx.x;
-  st_load_nid(nid, n, tile, ntiles, nd);
-  st_load_nid(nid, n, tile + stride, ntiles, nd1);
-  st_load_rec(rec, tile, nd, r);
-  st_load_idx(idx, tile, nd, ix);
-  for (int k = 0; tile < ntiles; tile += stride, ++k) {
-    st_load_nid(nid, n, tile + 2 * stride, ntiles, nd2);
-    st_load_rec(rec, tile + stride, nd1, r1);
-    st_load_idx(idx, tile + stride, nd1, ix1);
-    // per-node split bookkeeping of this tile's particles: independent of the flag scan, issued before its barriers
-    int nl[IPT], lb[IPT];
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-      nl[j] = 0; lb[j] = 0;
-      if (nd[j] >= 0) { nl[j] = __ldg(nleft + nd[j]); lb[j] = __ldg(lbase + nd[j]); }
-    }
-    const int tb = (int)tilebase[tile];
-    tile_flags_scan(nodes, nd, r, it, s_w[k & 1]);
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-      const int i = tile * TILE + j * TPB + (int)threadIdx.x;
-      if (i >= n) continue;
-      if (nd[j] < 0) { nid_out[i] = -1; continue; }
-      if (it[j].sp < 0 || nl[j] < 0) {   // finished leaf (or degenerate split): final position reached
-        src4[i] = r[j]; perm[i] = ix[j]; nid_out[i] = -1;
-        continue;
-      }
-      const int off = it[j].offset;
-      const int L = tb + it[j].excl - lb[j];       // left flags of this node before i
-      int dest, child;
-      if (it[j].flag) { dest = off + L; child = it[j].cl; }
-      else { dest = off + nl[j] + ((i - off) - L); child = it[j].cr; }
-      rec_out[dest] = r[j]; idx_out[dest] = ix[j]; nid_out[dest] = child;
-    }
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) { nd[j] = nd1[j]; nd1[j] = nd2[j]; r[j] = r1[j]; ix[j] = ix1[j]; }
-  }
 }
 
 // ---- monopole moments of internal nodes, bottom-up one level at a time (RCBForceTree.cxx:856-889) -------
@@ -820,46 +1014,32 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
   const int ppn = (int)(ppn64 > INT_MAX ? INT_MAX : ppn64);
   cudaStream_t st = c->stream;
   const int ntiles = (n + TILE - 1) / TILE;
-  // persistent grids of the tile kernels: as many blocks as are resident at once, each walking tiles with stride gridDim
-  static int occ_lc = 0, occ_sc = 0;
-  if (!occ_lc) {
-    HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sc, k_scatter, TPB, 0));
-    HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lc, k_left_count, TPB, 0));
-    if (occ_lc < 1 || occ_sc < 1) { occ_lc = 0; set_error("tile kernels do not fit on an SM"); return 2; }
+  // persistent grid of the split pass: as many blocks as are resident at once, each taking tiles by ticket
+  static int occ_sp = 0;
+  if (!occ_sp) {
+    HSR_CUDA(cudaFuncSetAttribute(k_split_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, NST * SLOT_BYTES));
+    HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sp, k_split_pass, TPB, (size_t)NST * SLOT_BYTES));
+    if (occ_sp < 1) { occ_sp = 0; set_error("k_split_pass does not fit on an SM"); return 2; }
   }
-  // experimental k_cm_warp (HACCSR_CM_KERNEL=warp): one contiguous range of particles per resident warp
-  int cmw_per_warp = 0, cmw_blocks = 0;
-  {
-    const char *e = getenv("HACCSR_CM_KERNEL");
-    if (e && !strcmp(e, "warp") && n > 0) {
-      int occ = 0;
-      HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cm_warp, TPB, 0));
-      const long long warps = (long long)c->sm_count * (occ > 0 ? occ : 1) * (TPB / 32);
-      const int step = 32 * CMW_ROWS;
-      long long pw = ((long long)n + warps - 1) / warps;
-      pw = (pw + step - 1) / step * step;
-      cmw_per_warp = (int)pw;
-      cmw_blocks = (int)(((long long)n + pw * (TPB / 32) - 1) / (pw * (TPB / 32)));
-    }
-  }
-  const int grid_lc = ntiles < c->sm_count * occ_lc ? (ntiles > 0 ? ntiles : 1) : c->sm_count * occ_lc;
-  const int grid_sc = ntiles < c->sm_count * occ_sc ? (ntiles > 0 ? ntiles : 1) : c->sm_count * occ_sc;
+  const int grid_sp = ntiles < c->sm_count * occ_sp ? (ntiles > 0 ? ntiles : 1) : c->sm_count * occ_sp;
   // node pool: every split node has > ppn particles and two non-empty children, so nodes <= 2N-1; in
   // practice ~4N/ppn.  Start generously and grow (rebuild) if the pool runs out.
   int64_t want_nodes = 1024 + 8 * (n64 / (ppn > 0 ? ppn : 1));
   if (want_nodes > 2 * n64 + 8) want_nodes = 2 * n64 + 8;
   if ((int64_t)c->nodes.cap > want_nodes) want_nodes = (int64_t)c->nodes.cap;
+  // nodes of one level: children of the previous level's split nodes, which hold > ppn particles each
+  const int64_t level_cap = 2 * (n64 / ((int64_t)ppn + 1)) + 2;
+  const int64_t nblk_cap = (level_cap + NTPB - 1) / NTPB + 1;
 
-  HSR_TRY(c->recA.ensure(n + 1)); HSR_TRY(c->recB.ensure(n + 1)); HSR_TRY(c->src4.ensure(n + 1));
-  HSR_TRY(c->idxA.ensure(n + 1)); HSR_TRY(c->idxB.ensure(n + 1)); HSR_TRY(c->perm.ensure(n + 1));
-  HSR_TRY(c->nidA.ensure(n + 1)); HSR_TRY(c->nidB.ensure(n + 1));
-  HSR_TRY(c->tilecount.ensure(ntiles + 1)); HSR_TRY(c->tilebase.ensure(ntiles + 1));
+  // (+8: the bulk copies of the last tile are rounded up to 16 bytes)
+  HSR_TRY(c->recA.ensure(n + 8)); HSR_TRY(c->recB.ensure(n + 8)); HSR_TRY(c->src4.ensure(n + 1));
+  HSR_TRY(c->idxA.ensure(n + 8)); HSR_TRY(c->idxB.ensure(n + 8)); HSR_TRY(c->perm.ensure(n + 1));
+  HSR_TRY(c->nidA.ensure(n + 8)); HSR_TRY(c->nidB.ensure(n + 8));
+  HSR_TRY(c->tile_desc.ensure((size_t)ntiles + 1)); HSR_TRY(c->node_desc.ensure((size_t)nblk_cap + 1));
   HSR_TRY(c->scratch_u32.ensure(16));
 
   for (int attempt = 0; attempt < 6; ++attempt) {
-    HSR_TRY(c->nodes.ensure(want_nodes)); HSR_TRY(c->acc.ensure(want_nodes));
-    HSR_TRY(c->lstart.ensure(want_nodes)); HSR_TRY(c->lend.ensure(want_nodes));
-    HSR_TRY(c->lbase.ensure(want_nodes)); HSR_TRY(c->nleft.ensure(want_nodes));
+    HSR_TRY(c->nodes.ensure(want_nodes)); HSR_TRY(c->acc.ensure(want_nodes)); HSR_TRY(c->tot.ensure(want_nodes));
     const int max_nodes = (int)(c->nodes.cap > (size_t)INT_MAX ? INT_MAX : c->nodes.cap);
     unsigned *maxima = c->scratch_u32.p;
     float *scales = reinterpret_cast<float *>(c->scratch_u32.p + 4);
@@ -867,64 +1047,70 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
     c->n_tree = n; c->n_nodes = 1; c->n_levels = 0;
     if (n == 0) {
       k_root_init<<<1, 1, 0, st>>>(c->nodes.p, c->acc.p, 0, make_float3(lo[0], lo[1], lo[2]),
-                                   make_float3(hi[0], hi[1], hi[2]), maxima, scales, c->d_level);
+                                   make_float3(hi[0], hi[1], hi[2]), maxima, scales, c->d_state);
       c->launches++;
       HSR_CUDA(cudaGetLastError());
       c->level_begin[0] = 0; c->level_end[0] = 1; c->n_levels = 1; c->unit_mass = false;
       return 0;
     }
+    HSR_CUDA(cudaMemsetAsync(c->tile_desc.p, 0, ((size_t)ntiles + 1) * sizeof(unsigned long long), st));
+    HSR_CUDA(cudaMemsetAsync(c->node_desc.p, 0, ((size_t)nblk_cap + 1) * sizeof(unsigned long long), st));
     int grid_lin = (n + TPB - 1) / TPB;
     if (grid_lin > c->sm_count * 16) grid_lin = c->sm_count * 16;
     k_init_records<<<grid_lin, TPB, 0, st>>>(c->cur.x, c->cur.y, c->cur.z, c->cur.mass, n, c->recA.p, c->idxA.p,
                                              c->nidA.p, maxima);
     k_root_init<<<1, 1, 0, st>>>(c->nodes.p, c->acc.p, n, make_float3(lo[0], lo[1], lo[2]),
-                                 make_float3(hi[0], hi[1], hi[2]), maxima, scales, c->d_level);
-    c->launches += 2;
+                                 make_float3(hi[0], hi[1], hi[2]), maxima, scales, c->d_state);
+    k_cm_tile<<<(n + CM_TILE - 1) / CM_TILE, TPB, 0, st>>>(c->recA.p, c->nidA.p, n, c->acc.p, scales);
+    c->launches += 3;
     HSR_CUDA(cudaGetLastError());
 
     float4 *rec = c->recA.p, *rec_o = c->recB.p;
     unsigned *idx = c->idxA.p, *idx_o = c->idxB.p;
     int *nid = c->nidA.p, *nid_o = c->nidB.p;
-    int begin = 0, end = 1, nnodes = 1, level = 0;
+    // The levels are queued without waiting for each other's outcome: a launch for a level the tree does not have returns
+    // at once (BuildState::nsplit).  The host looks at the state after the expected depth and then every two levels.
+    int depth = 0;
+    {
+      int64_t q = n64 / (ppn > 0 ? ppn : 1);
+      int lg = 0;
+      while (((int64_t)1 << lg) < q) ++lg;
+      depth = lg + 2;
+    }
+    int level = 0, n_levels = 0;
     bool overflow = false;
-    for (;; ++level) {
-      if (level >= 127) { set_error("tree deeper than 127 levels"); return 1; }
-      c->level_begin[level] = begin; c->level_end[level] = end;
-      if (cmw_per_warp) k_cm_warp<<<cmw_blocks, TPB, 0, st>>>(rec, nid, n, cmw_per_warp, c->acc.p, scales);
-      else k_cm_tile<<<(n + CM_TILE - 1) / CM_TILE, TPB, 0, st>>>(rec, nid, n, c->acc.p, scales);
-      {
-        const int nl = end - begin, gb = (nl + 255) / 256;
-        HSR_TRY(c->split_flag.ensure((size_t)nl + 1)); HSR_TRY(c->split_rank.ensure((size_t)nl + 1));
-        k_level_decide<<<gb, 256, 0, st>>>(c->nodes.p, c->acc.p, begin, end, ppn, scales, c->split_flag.p, c->d_level);
-        HSR_TRY(scan_exclusive(c, c->split_flag.p, c->split_rank.p, nl, c->d_counters + 13));
-        k_level_children<<<gb, 256, 0, st>>>(c->nodes.p, c->acc.p, begin, end, nnodes, max_nodes, c->split_flag.p,
-                                             c->split_rank.p, c->d_counters + 13, c->d_level);
+    while (!n_levels && !overflow) {
+      if (depth > 127) depth = 127;
+      for (; level < depth; ++level) {
+        int64_t nl_cap = level < 40 ? ((int64_t)1 << level) : level_cap;
+        if (nl_cap > level_cap) nl_cap = level_cap;
+        const int gb = (int)((nl_cap + NTPB - 1) / NTPB);
+        k_level_nodes<<<gb < 1 ? 1 : gb, NTPB, 0, st>>>(c->nodes.p, c->acc.p, c->tot.p, c->d_state, c->node_desc.p, level, ppn,
+                                                        max_nodes, scales);
+        {
+          // cooperative launch: the look-back needs every block of the grid resident (the launch fails instead of hanging)
+          const float4 *a0 = rec; const unsigned *a1 = idx; const int *a2 = nid; Node *a3 = c->nodes.p; NodeAcc *a4 = c->acc.p;
+          const float *a5 = scales; BuildState *a6 = c->d_state; unsigned long long *a7 = c->tile_desc.p;
+          int a8 = level, a9 = n, a10 = ntiles; float4 *a11 = rec_o; unsigned *a12 = idx_o; int *a13 = nid_o;
+          float4 *a14 = c->src4.p; unsigned *a15 = c->perm.p;
+          void *args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11, &a12, &a13, &a14, &a15};
+          HSR_CUDA(cudaLaunchCooperativeKernel((const void *)k_split_pass, dim3(grid_sp), dim3(TPB), args, (size_t)NST * SLOT_BYTES, st));
+        }
+        c->launches += 2;
+        float4 *tr = rec; rec = rec_o; rec_o = tr;
+        unsigned *ti = idx; idx = idx_o; idx_o = ti;
+        int *tn = nid; nid = nid_o; nid_o = tn;
       }
-      c->launches += 3;
-      HSR_CUDA(cudaMemcpyAsync(c->h_level, c->d_level, sizeof(LevelInfo), cudaMemcpyDeviceToHost, st));
-      HSR_CUDA(cudaStreamSynchronize(st));
-      LevelInfo li = *c->h_level;
-      if (level == 0) c->unit_mass = li.unit_mass != 0;
-      if (li.error) { overflow = true; break; }
-      if (li.nsplit > 0) {
-        k_left_count<<<grid_lc, TPB, 0, st>>>(rec, nid, c->nodes.p, n, ntiles, c->tilecount.p, c->lstart.p, c->lend.p);
-        c->launches++;
-        HSR_TRY(scan_exclusive(c, c->tilecount.p, c->tilebase.p, ntiles, nullptr));
-        int nl = end - begin;
-        k_set_children<<<(nl + 255) / 256, 256, 0, st>>>(c->nodes.p, begin, end, c->tilebase.p, c->lstart.p,
-                                                          c->lend.p, c->lbase.p, c->nleft.p);
-        c->launches++;
-      }
-      k_scatter<<<grid_sc, TPB, 0, st>>>(rec, idx, nid, c->nodes.p, n, ntiles, c->tilebase.p, c->lbase.p, c->nleft.p, rec_o,
-                                        idx_o, nid_o, c->src4.p, c->perm.p);
-      c->launches++;
       HSR_CUDA(cudaGetLastError());
-      nnodes = li.end;
-      if (li.nsplit == 0) break;
-      begin = li.begin; end = li.end;
-      float4 *tr = rec; rec = rec_o; rec_o = tr;
-      unsigned *ti = idx; idx = idx_o; idx_o = ti;
-      int *tn = nid; nid = nid_o; nid_o = tn;
+      HSR_CUDA(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(BuildState), cudaMemcpyDeviceToHost, st));
+      HSR_CUDA(cudaStreamSynchronize(st));
+      const BuildState &S = *c->h_state;
+      if (S.error) { overflow = true; break; }
+      for (int L = 0; L < level; ++L) if (S.nsplit[L] == 0) { n_levels = L + 1; break; }
+      if (!n_levels) {
+        if (level >= 127) { set_error("tree deeper than 127 levels"); return 1; }
+        depth = level + 2;
+      }
     }
     if (overflow) {
       if ((int64_t)c->nodes.cap >= 2 * n64 + 8) { set_error("node pool exhausted at its upper bound"); return 1; }
@@ -933,7 +1119,12 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
       // DevBuf::ensure reallocates (contents are rebuilt from scratch on the next attempt)
       continue;
     }
-    c->n_nodes = nnodes; c->n_levels = level + 1;
+    {
+      const BuildState &S = *c->h_state;
+      c->n_levels = n_levels; c->n_nodes = S.lvl_end[n_levels - 1]; c->unit_mass = S.unit_mass != 0;
+      for (int L = 0; L < n_levels; ++L) { c->level_begin[L] = S.lvl_begin[L]; c->level_end[L] = S.lvl_end[L]; }
+    }
+    const int nnodes = c->n_nodes;
     for (int L = c->n_levels - 2; L >= 0; --L) {
       int nl = c->level_end[L] - c->level_begin[L];
       k_moments<<<(nl + 255) / 256, 256, 0, st>>>(c->nodes.p, c->src4.p, c->level_begin[L], c->level_end[L]);

@@ -87,7 +87,10 @@ def check_accel(out, o, o64, og, tag="", of=None):
     r_cpu, _, _, _ = accel_errors(b, c)
     assert np.median(rel) <= 5e-6, tag
     assert np.quantile(rel, 0.99) <= 1e-4, tag
-    assert np.quantile(r_gpu, 0.999) <= slack * np.quantile(r_cpu, 0.999) + 1e-7, (tag, np.quantile(r_gpu, 0.999), np.quantile(r_cpu, 0.999))
+    # tail quantile with at least 50 particles beyond it (the 99.9th percentile of a 4096-particle case is its 4th largest value:
+    # noise between two summation orders)
+    qt = min(0.999, 1.0 - 50.0 / max(r_gpu.size, 100))
+    assert np.quantile(r_gpu, qt) <= slack * np.quantile(r_cpu, qt) + 1e-7, (tag, qt, np.quantile(r_gpu, qt), np.quantile(r_cpu, qt))
     assert np.median(r_gpu) <= slack * np.median(r_cpu) + 1e-8, (tag, np.median(r_gpu), np.median(r_cpu))
 
 
