@@ -266,8 +266,14 @@ static constexpr unsigned long long ST_AGG = 1ull, ST_PREFIX = 2ull;
 __device__ __forceinline__ unsigned long long desc_make(unsigned epoch, unsigned long long status, unsigned v) {
   return ((unsigned long long)epoch << 34) | (status << 32) | (unsigned long long)v;
 }
-__device__ __forceinline__ void desc_store(unsigned long long *p, unsigned long long w) { *(volatile unsigned long long *)p = w; }
-__device__ __forceinline__ unsigned long long desc_load(const unsigned long long *p) { return *(const volatile unsigned long long *)p; }
+__device__ __forceinline__ void desc_store(unsigned long long *p, unsigned long long w) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long desc_load(const unsigned long long *p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
 
 // Warp-collective: the sum of the values of descriptors pos, pos-1, ... down to and including the nearest inclusive prefix.
 // W windows of 32 descriptors are read at once (one L2 round trip for a look-back of 32*W tiles); a word that is not
@@ -457,7 +463,6 @@ __global__ void __launch_bounds__(NTPB) k_level_nodes(Node *__restrict__ nodes, 
 static constexpr int NSLOT = 32;       // children of one tile accumulated in shared memory (more: straight to global)
 static constexpr int LB_W = 8;         // look-back windows read at once
 static constexpr int NST = 4;          // tiles of the shared-memory ring: B stage, A stage, two in flight
-static constexpr int SLOT_REC = 0, SLOT_IDX = TILE * 16, SLOT_NID = TILE * 20, SLOT_BYTES = TILE * 24;
 
 __device__ __forceinline__ unsigned tb_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tb_mbar_init(unsigned bar, unsigned count) {
@@ -498,14 +503,18 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 // Publishing a tile's count in the same iteration that consumes its predecessors' counts makes all blocks march in step
 // and leaves the warps waiting at the barrier behind the look-back (measured: 54 % of all stall samples, 0.7 ms per
 // level); with the count one iteration ahead a block can run an iteration ahead of its neighbours.
-__global__ void __launch_bounds__(TPB, 2) k_split_pass(const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
+template <int PTPB>
+__global__ void __launch_bounds__(PTPB, 512 / PTPB) k_split_pass(const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
                                                        const int *__restrict__ nid, Node *__restrict__ nodes,
                                                        NodeAcc *__restrict__ acc, const float *__restrict__ scales,
                                                        BuildState *__restrict__ st, unsigned long long *__restrict__ desc,
                                                        int level, int n, int ntiles, float4 *__restrict__ rec_out,
                                                        unsigned *__restrict__ idx_out, int *__restrict__ nid_out,
                                                        float4 *__restrict__ src4, unsigned *__restrict__ perm) {
-  static_assert(IPT * (TPB / 32) == 32, "one warp scans the per-(row, warp) entries");
+  constexpr int PT = PTPB * IPT;                       // particles per tile
+  constexpr int NE = IPT * (PTPB / 32);                // (row, warp) entries of a tile
+  constexpr int SLOT_REC = 0, SLOT_IDX = PT * 16, SLOT_NID = PT * 20, SLOT_BYTES = PT * 24;
+  static_assert(NE <= 32, "one warp scans the per-(row, warp) entries");
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ unsigned s_fb[NST][32], s_hb[NST][32];   // per slot and (row, warp) entry: ballots of the left flags and of the node starts
   __shared__ int s_cv[NST][32], s_cf[NST][32];        // per slot: exclusive segmented scan of the entries
@@ -525,13 +534,14 @@ __global__ void __launch_bounds__(TPB, 2) k_split_pass(const float4 *__restrict_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (t < NSLOT) slot_reset(slots[t]);
+  if (t < 32) { s_ev[t] = 0; s_ef[t] = 0; }           // entries beyond NE stay neutral in the scan
   __syncthreads();
   // one thread posts the three bulk copies of tile number k of this block
   auto issue = [&](int k) {
     const int T = T00 + k * G;
     if (T >= ntiles) return;
-    const int q = k % NST, i0 = T * TILE;
-    const int cnt = min(TILE, n - i0);
+    const int q = k % NST, i0 = T * PT;
+    const int cnt = min(PT, n - i0);
     const unsigned b4 = (unsigned)(((cnt * 4) + 15) & ~15);
     const unsigned bar = tb_smem_u32(&s_bar[q]), base = tb_smem_u32(ring + (size_t)q * SLOT_BYTES);
     s_misc[q][0] = 0; s_misc[q][1] = INT_MAX;
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(TPB, 2) k_split_pass(const float4 *__restrict_
   };
   // A stage of tile number k: flags, node starts, ballots, entries (consumed by warp 0 behind the next barrier)
   auto stage_a = [&](int k) {
-    const int T = T00 + k * G, q = k % NST, tile0 = T * TILE;
+    const int T = T00 + k * G, q = k % NST, tile0 = T * PT;
     tb_mbar_wait(tb_smem_u32(&s_bar[q]), (unsigned)((k / NST) & 1));
     const unsigned char *sl = ring + (size_t)q * SLOT_BYTES;
     const int *nidS = reinterpret_cast<const int *>(sl + SLOT_NID);
@@ -551,15 +561,14 @@ __global__ void __launch_bounds__(TPB, 2) k_split_pass(const float4 *__restrict_
     int cmin = INT_MAX;
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
-      const int p = j * TPB + t, i = tile0 + p;
+      const int p = j * PTPB + t, i = tile0 + p;
       int flag = 0, head = 0;
       const int ndv = i < n ? nidS[p] : -1;
       if (ndv >= 0) {
         const float4 *np = reinterpret_cast<const float4 *>(nodes + ndv);
-        const float4 a = __ldg(np);
+        const float4 a = __ldg(np), c = __ldg(np + 2), d = __ldg(np + 3);     // independent loads: one L2 round trip
         const int cl = __float_as_int(a.z);
         if (cl > 0) {                                                            // the node splits at this level
-          const float4 c = __ldg(np + 2), d = __ldg(np + 3);
           const int sp = __float_as_int(d.w) & 3, off = __float_as_int(a.y);
           const float pivot = sp == 0 ? c.z : (sp == 1 ? c.w : d.x);             // xc[sp], RCBForceTree.cxx:720
           flag = recS[4 * p + sp] < pivot;                                       // :640
@@ -570,7 +579,7 @@ __global__ void __launch_bounds__(TPB, 2) k_split_pass(const float4 *__restrict_
       }
       const unsigned fb = __ballot_sync(0xffffffffu, flag), hb = __ballot_sync(0xffffffffu, head);
       if (lane == 0) {
-        const int e = j * (TPB / 32) + w;
+        const int e = j * (PTPB / 32) + w;
         s_fb[q][e] = fb; s_hb[q][e] = hb;
         s_ev[e] = hb ? __popc(fb >> (31 - __clz(hb))) : __popc(fb);
         s_ef[e] = hb != 0u;
@@ -604,7 +613,7 @@ __global__ void __launch_bounds__(TPB, 2) k_split_pass(const float4 *__restrict_
   if (w == 0 && nk > 0) scan_publish(0);
   __syncthreads();
   for (int k = 0; k < nk; ++k) {
-    const int T0 = T00 + k * G, q = k % NST, tile0 = T0 * TILE;
+    const int T0 = T00 + k * G, q = k % NST, tile0 = T0 * PT;
     if (t == 0) issue(k + NST - 1);           // its slot was tile k-1's: every thread left it before the last barrier
     if (k + 1 < nk) stage_a(k + 1);
     __syncthreads();
@@ -630,19 +639,18 @@ __global__ void __launch_bounds__(TPB, 2) k_split_pass(const float4 *__restrict_
     unsigned fl = 0;         // bit j: left flag of item j
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
-      const int p = j * TPB + t, i = tile0 + p;
+      const int p = j * PTPB + t, i = tile0 + p;
       cl[j] = 0;
       if (i >= n) continue;
       const int ndv = nidS[p];
       if (ndv < 0) { nid_out[i] = -1; continue; }
       const float4 *np = reinterpret_cast<const float4 *>(nodes + ndv);
-      const float4 a = __ldg(np);
+      const float4 a = __ldg(np), d = __ldg(np + 3);
       int cnt = __float_as_int(a.x), off = __float_as_int(a.y);
       cl[j] = __float_as_int(a.z);
       r[j] = recS[p];
       const unsigned ix = idxS[p];
       if (cl[j] <= 0) {                      // the node is a leaf (or an orphan holding a degenerate node's particles): final place
-        const float4 d = __ldg(np + 3);
         int fin = i;
         if (__float_as_int(d.w) == -2) {     // reversed: mirror the leaf (an orphan has its parent's range)
           if (cnt == 0) {
@@ -654,7 +662,7 @@ __global__ void __launch_bounds__(TPB, 2) k_split_pass(const float4 *__restrict_
         src4[fin] = r[j]; perm[fin] = ix; nid_out[i] = -1;
         continue;
       }
-      const int e = j * (TPB / 32) + w;
+      const int e = j * (PTPB / 32) + w;
       const unsigned fb = s_fb[q][e], hb = s_hb[q][e];
       const unsigned hm = hb & (below | (1u << lane));      // node starts at or before this lane in its row
       int lb;
@@ -1013,14 +1021,21 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
   const int n = (int)n64;
   const int ppn = (int)(ppn64 > INT_MAX ? INT_MAX : ppn64);
   cudaStream_t st = c->stream;
-  const int ntiles = (n + TILE - 1) / TILE;
-  // persistent grid of the split pass: as many blocks as are resident at once, each taking tiles by ticket
-  static int occ_sp = 0;
-  if (!occ_sp) {
-    HSR_CUDA(cudaFuncSetAttribute(k_split_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, NST * SLOT_BYTES));
-    HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sp, k_split_pass, TPB, (size_t)NST * SLOT_BYTES));
+  // split pass geometry: 256 threads x 4 particles (1024-particle tiles, two blocks per SM); HACCSR_PASS_TPB=128 selects
+  // 512-particle tiles, four blocks per SM (measured: the same 7.6 ms per build at 21.5 M particles)
+  static int ptpb = 0, occ_sp = 0;
+  if (!ptpb) {
+    const char *e = getenv("HACCSR_PASS_TPB");
+    const int want = (e && atoi(e) == 128) ? 128 : 256;
+    const void *fn = want == 256 ? (const void *)k_split_pass<256> : (const void *)k_split_pass<128>;
+    const size_t dyn = (size_t)NST * want * IPT * 24;
+    HSR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sp, fn, want, dyn));
     if (occ_sp < 1) { occ_sp = 0; set_error("k_split_pass does not fit on an SM"); return 2; }
+    ptpb = want;
   }
+  const int PT = ptpb * IPT;
+  const int ntiles = (n + PT - 1) / PT;
   const int grid_sp = ntiles < c->sm_count * occ_sp ? (ntiles > 0 ? ntiles : 1) : c->sm_count * occ_sp;
   // node pool: every split node has > ppn particles and two non-empty children, so nodes <= 2N-1; in
   // practice ~4N/ppn.  Start generously and grow (rebuild) if the pool runs out.
@@ -1094,7 +1109,8 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
           int a8 = level, a9 = n, a10 = ntiles; float4 *a11 = rec_o; unsigned *a12 = idx_o; int *a13 = nid_o;
           float4 *a14 = c->src4.p; unsigned *a15 = c->perm.p;
           void *args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11, &a12, &a13, &a14, &a15};
-          HSR_CUDA(cudaLaunchCooperativeKernel((const void *)k_split_pass, dim3(grid_sp), dim3(TPB), args, (size_t)NST * SLOT_BYTES, st));
+          const void *fn = ptpb == 256 ? (const void *)k_split_pass<256> : (const void *)k_split_pass<128>;
+          HSR_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid_sp), dim3(ptpb), args, (size_t)NST * PT * 24, st));
         }
         c->launches += 2;
         float4 *tr = rec; rec = rec_o; rec_o = tr;
