@@ -67,6 +67,8 @@ def parse():
                     help="sub-cycles per long step for the Level-2 end-to-end path (haccsr_subcycle; reference indat nsub = 5); 0 = skip")
     ap.add_argument("--cull", action="store_true", help="headline run with warp-level culling on (haccsr_set_culling); "
                     "by default culling is off and only a side measurement of it is reported under 'culled'")
+    ap.add_argument("--no-refresh-block", action="store_true",
+                    help="skip the side block 'refresh' (overload refresh of one global snapshot decomposed over the ranks, configs[3])")
     ap.add_argument("--tune-ppn", default="", help="comma-separated leaf sizes for the side block 'tuned' (time to solution per kick)")
     return ap.parse_args()
 
@@ -500,6 +502,8 @@ def main():
     if args.tune_ppn:
         tuned = B.tuned([int(t) for t in args.tune_ppn.split(",")], stc["pairs_in_cutoff"])
     p_head, nglt_head = B.p, B.nglt
+    if args.no_cpu_baseline or world != 1:
+        p_head = None
 
     # ---- the clustered target state as a side block (configs[2]) -------------------------------------------
     clustered = None
@@ -513,6 +517,18 @@ def main():
         if args.arith == "fused":
             clustered["culled"] = B.culled(acc_c["ms_force"] / steps_c)
     B.g.close()
+    B.g = None
+    del B.pin, B.work, B.p
+    torch.cuda.empty_cache()
+
+    # ---- overload refresh of ONE global snapshot cut into the ranks' sub-volumes (configs[3]; 1x1x1 / 2x1x1 / 2x2x1 / 2x2x2) ------
+    refresh = None
+    if not args.no_refresh_block and world in (1, 2, 4, 8):
+        from tools import decomposed
+        try:
+            refresh = decomposed.refresh_block(args.np_side, GHOST, rank, world, local, dist)
+        except Exception as ex:      # a side block must not take the headline down
+            refresh = {"error": repr(ex)}
 
     if rank != 0:
         if dist is not None:
@@ -530,6 +546,8 @@ def main():
         line["tuned"] = tuned
     if clustered:
         line["clustered"] = clustered
+    if refresh:
+        line["refresh"] = refresh
     if args.cull:
         # with culling the kernel executes 30 flop only for the pairs that reach the force law and 9 (three differences,
         # the r2 chain, the softening add) for the rest: report the executed rate next to the algorithmic one

@@ -6,7 +6,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 HOST = os.path.join(_HERE, "host")
-SOURCES = ["api.cu", "tree_build.cu", "walk.cu", "force.cu", "refresh.cu", "cic.cu"]
+SOURCES = ["api.cu", "tree_build.cu", "walk.cu", "force.cu", "refresh.cu", "exchange.cu", "cic.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -31,7 +31,7 @@ def build(force=False, verbose=False):
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
                                                        os.path.join(_HERE, "..", "include", "haccsr.h")]
     if force or _stale(out, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         subprocess.check_call(cmd)

@@ -33,6 +33,20 @@ class KickStats(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class RefreshStats(C.Structure):
+    _fields_ = [("alive", C.c_int64), ("ghosts", C.c_int64), ("sent", C.c_int64), ("bytes_sent", C.c_int64),
+                ("bytes_received", C.c_int64), ("bytes_sent_remote", C.c_int64), ("messages_received", C.c_int32),
+                ("reserved", C.c_int32), ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_ if f != "reserved"}
+
+
+class Map2(C.Structure):
+    _fields_ = [("tree_lo", C.c_float * 3), ("tree_hi", C.c_float * 3), ("force_lo", C.c_float * 3), ("force_hi", C.c_float * 3),
+                ("fcoeff", C.c_float)]
+
+
 class KickOpts(C.Structure):
     _fields_ = [("count_in_cutoff", C.c_int32), ("skip_force", C.c_int32), ("reserved", C.c_int32 * 6)]
 
@@ -79,6 +93,11 @@ def load_library():
     lib.haccsr_subcycle.argtypes = [vp, C.c_int, C.c_float, fp, fp, fp, fp, fp, C.c_float, C.c_int64, C.c_int, C.c_float,
                                     C.POINTER(KickStats)]
     i32p = C.POINTER(C.c_int32)
+    lib.haccsr_map2_setup.argtypes = [i32p, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double, C.POINTER(Map2)]
+    lib.haccsr_map1_factor.restype = C.c_float
+    lib.haccsr_map1_factor.argtypes = [C.c_float] * 4
+    lib.haccsr_particles_subcycle.argtypes = [vp, C.c_int, i32p, C.c_float, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double,
+                                              C.c_double, C.c_double, C.c_float, C.c_int64, C.c_int, C.POINTER(KickStats)]
     lib.haccsr_cic.argtypes = [vp, i32p, C.c_float, vp, C.c_int]
     lib.haccsr_inverse_cic.argtypes = [vp, i32p, vp, C.c_int, C.c_float, C.c_float, C.c_int]
     lib.haccsr_refresh_message_bytes.restype = C.c_int64
@@ -86,6 +105,10 @@ def load_library():
     lib.haccsr_refresh_begin.argtypes = [vp, fp, fp, C.c_float, i32p, ip64, ip64]
     lib.haccsr_refresh_pack.argtypes = [vp, ip64, vp]
     lib.haccsr_refresh_append.argtypes = [vp, vp, C.c_int64]
+    lib.haccsr_refresh.argtypes = [vp, vp, i32p, C.c_int32, fp, fp, C.c_float, C.POINTER(RefreshStats)]
+    lib.haccsr_nccl_unique_id.argtypes = [vp]
+    lib.haccsr_nccl_comm_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp]
+    lib.haccsr_nccl_comm_destroy.argtypes = [vp]
     lib.haccsr_resident.restype = C.c_int64
     lib.haccsr_resident.argtypes = [vp]
     lib.haccsr_get_tree.argtypes = [vp, C.c_int64, ip64, i32p, i32p, i32p, i32p, fp]
@@ -99,8 +122,9 @@ def load_library():
 EXPORTS = ["haccsr_last_error", "haccsr_device_count", "haccsr_create", "haccsr_destroy", "haccsr_set_stream",
            "haccsr_set_force_law", "haccsr_set_arithmetic", "haccsr_set_culling", "haccsr_upload", "haccsr_download", "haccsr_host_register",
            "haccsr_host_unregister", "haccsr_kick", "haccsr_kick_host", "haccsr_stream", "haccsr_partition_in_box",
-           "haccsr_fill_mass", "haccsr_subcycle", "haccsr_cic", "haccsr_inverse_cic", "haccsr_refresh_message_bytes", "haccsr_refresh_begin",
-           "haccsr_refresh_pack", "haccsr_refresh_append", "haccsr_resident", "haccsr_get_tree", "haccsr_get_pseudo_particles",
+           "haccsr_fill_mass", "haccsr_subcycle", "haccsr_map2_setup", "haccsr_map1_factor", "haccsr_particles_subcycle", "haccsr_cic", "haccsr_inverse_cic", "haccsr_refresh_message_bytes", "haccsr_refresh_begin",
+           "haccsr_refresh_pack", "haccsr_refresh_append", "haccsr_refresh", "haccsr_nccl_unique_id", "haccsr_nccl_comm_create",
+           "haccsr_nccl_comm_destroy", "haccsr_resident", "haccsr_get_tree", "haccsr_get_pseudo_particles",
            "haccsr_get_lists"]
 
 _F32 = ("x", "y", "z", "vx", "vy", "vz", "mass", "phi")
@@ -227,6 +251,14 @@ class HaccSR:
                                              _f3(force_lo), _f3(force_hi), theta, int(ppn), tdpts, fcoeff, C.byref(st)))
         return st.as_dict()
 
+    def particles_subcycle(self, nsub, nglt, edge, gpscal, alpha, pp, adot, tau, tau2, fscal, theta, ppn, tdpts=1):
+        """Particles::subCycle from the TimeStepper's scalars (haccsr_particles_subcycle)."""
+        st = KickStats()
+        n3 = (C.c_int32 * 3)(*[int(t) for t in nglt])
+        self._check(self.lib.haccsr_particles_subcycle(self._h, int(nsub), n3, edge, gpscal, alpha, pp, adot, tau, tau2, fscal,
+                                                       theta, int(ppn), tdpts, C.byref(st)))
+        return st.as_dict()
+
     # ---- PM coupling (csrc/cic.cu) ----
     def cic(self, ng, c):
         """Particles::cic on the resident particles; returns the (ng0, ng1, ng2) float32 density grid."""
@@ -262,6 +294,15 @@ class HaccSR:
     def refresh_append(self, message_ptr, n):
         self._check(self.lib.haccsr_refresh_append(self._h, C.c_void_p(message_ptr), int(n)))
         self.n = self.resident()
+
+    def refresh(self, comm, dims, rank, alive_lo, alive_hi, ol):
+        """haccsr_refresh: the whole overload refresh of this rank (collective over `comm`, an NcclComm or None for 1x1x1)."""
+        st = RefreshStats()
+        d3 = (C.c_int32 * 3)(*[int(t) for t in dims])
+        self._check(self.lib.haccsr_refresh(self._h, comm.handle if comm is not None else None, d3, int(rank), _f3(alive_lo),
+                                            _f3(alive_hi), float(ol), C.byref(st)))
+        self.n = self.resident()
+        return st.as_dict()
 
     def resident(self):
         return int(self.lib.haccsr_resident(self._h))
@@ -299,3 +340,44 @@ class HaccSR:
                                               C.byref(nn), C.byref(nr), C.byref(npool), off.ctypes.data_as(u32p),
                                               ranges.ctypes.data_as(u32p), _fp(pool)))
         return {"range_off": off, "ranges": ranges[:nr.value], "pool": pool[:npool.value]}
+
+
+class NcclComm:
+    """An ncclComm_t created by libhaccsr (haccsr_nccl_comm_create) for haccsr_refresh.  `broadcast` moves the 128-byte id
+    from rank 0 to every rank: a callable bytes -> bytes (torch.distributed in bench.py, MPI_Bcast in a HACC rank)."""
+
+    def __init__(self, device, nranks, rank, broadcast):
+        self.lib = load_library()
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            rc = self.lib.haccsr_nccl_unique_id(buf)
+            if rc != 0:
+                raise HaccSRError("libhaccsr: %s (status %d)" % (self.lib.haccsr_last_error().decode(), rc))
+        ident = broadcast(bytes(buf))
+        buf = (C.c_ubyte * 128).from_buffer_copy(ident)
+        h = C.c_void_p()
+        rc = self.lib.haccsr_nccl_comm_create(C.byref(h), int(device), int(nranks), int(rank), buf)
+        if rc != 0:
+            raise HaccSRError("libhaccsr: %s (status %d)" % (self.lib.haccsr_last_error().decode(), rc))
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            self.lib.haccsr_nccl_comm_destroy(self.handle)
+            self.handle = None
+
+
+def map2_setup(nglt, edge, gpscal, fscal, tau, step_fraction):
+    """haccsr_map2_setup: the boxes and the kick coefficient Particles::map2 hands to the tree (host arithmetic only)."""
+    lib = load_library()
+    m = Map2()
+    n3 = (C.c_int32 * 3)(*[int(t) for t in nglt])
+    rc = lib.haccsr_map2_setup(n3, edge, gpscal, fscal, tau, step_fraction, C.byref(m))
+    if rc != 0:
+        raise HaccSRError(lib.haccsr_last_error().decode())
+    return {"tree_lo": list(m.tree_lo), "tree_hi": list(m.tree_hi), "force_lo": list(m.force_lo), "force_hi": list(m.force_hi),
+            "fcoeff": float(m.fcoeff)}
+
+
+def map1_factor(pp, tau, adot, alpha):
+    return float(load_library().haccsr_map1_factor(pp, tau, adot, alpha))

@@ -2,6 +2,7 @@
 // the small HBM-bound helpers around it (stream = Particles::map1, out-of-box compaction, mass fill).
 #include "common.cuh"
 
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -92,6 +93,7 @@ int compact_by_flags(haccsr_ctx *c, const unsigned *flag, unsigned *pref, int64_
   k_compact<<<lin_grid(c, n), 256, 0, c->stream>>>(c->cur, c->alt, flag, pref, (unsigned)nin, (long long)n);
   HSR_CUDA(cudaGetLastError());
   Soa t = c->cur; c->cur = c->alt; c->alt = t;
+  c->order_epoch++;
   if (n_kept) *n_kept = nin;
   return 0;
 }
@@ -150,6 +152,7 @@ int haccsr_create(haccsr_ctx **out, int device, int64_t max_particles) {
     if (cudaMalloc((void **)&c->d_state, sizeof(BuildState)) != cudaSuccess) { rc = 2; break; }
     if (cudaMallocHost((void **)&c->h_counters, 32 * sizeof(int64_t)) != cudaSuccess) { rc = 2; break; }
     if (cudaMalloc((void **)&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) { rc = 2; break; }
+    if (cudaMalloc((void **)&c->d_slotcount, 32 * sizeof(long long)) != cudaSuccess) { rc = 2; break; }
     for (int i = 0; i < 5; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { rc = 2; break; }
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = 2; break; }
     if (cudaEventCreateWithFlags(&c->ev_up2, cudaEventDisableTiming) != cudaSuccess) { rc = 2; break; }
@@ -183,6 +186,8 @@ int haccsr_destroy(haccsr_ctx *c) {
   if (c->d_state) cudaFree(c->d_state);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->d_counters) cudaFree(c->d_counters);
+  if (c->d_slotcount) cudaFree(c->d_slotcount);
+  c->refresh_cand.release(); c->xchg_send.release(); c->xchg_recv.release(); c->xchg_table.release();
   for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->ev_up2) cudaEventDestroy(c->ev_up2);
   if (c->ev_built) cudaEventDestroy(c->ev_built);
@@ -290,6 +295,7 @@ int haccsr_upload(haccsr_ctx *c, int64_t n, const float *x, const float *y, cons
   if (mask) { COPY_H2D(c->cur.mask, mask, (size_t)n * sizeof(uint16_t)); } else { HSR_CUDA(cudaMemsetAsync(c->cur.mask, 0, (size_t)n * sizeof(uint16_t), c->stream)); }
   HSR_CUDA(cudaStreamSynchronize(c->stream));
   c->n_resident = n;
+  c->order_epoch++;
   return 0;
 }
 
@@ -457,12 +463,14 @@ int haccsr_kick_host(haccsr_ctx *c, int64_t n, float *x, float *y, float *z, flo
   HSR_CUDA(cudaEventRecord(c->ev_up2, cs));
   c->wait_up2 = true;
   c->n_resident = n;
+  c->order_epoch++;
   // inside kick_impl the copy stream takes the seven arrays the force kernel leaves alone as soon as the build
   // has permuted them; the velocities follow the force kernel on the main stream
   const HostOut ho = {x, y, z, vx, vy, vz, mass, phi, id, mask};
   int rc = kick_impl(c, n, tree_lo, tree_hi, force_lo, force_hi, theta, ppn, tdpts, fcoeff, opts, stats, &ho);
   if (c->wait_up2) { c->wait_up2 = false; cudaStreamWaitEvent(s, c->ev_up2, 0); }   // n == 0 or an early error
   cudaStreamSynchronize(cs);
+  if (rc) c->n_resident = 0;      // the device arrays may be partly uploaded / partly permuted: nothing usable is resident
   return rc;
 }
 
@@ -527,6 +535,43 @@ int haccsr_subcycle(haccsr_ctx *c, int nsub, float pt, const float box_hi[3], co
   return 0;
 }
 
+int haccsr_map2_setup(const int32_t nglt[3], float edge, float gpscal, double fscal, double tau, double step_fraction,
+                      haccsr_map2 *out) {
+  if (!nglt || !out) { set_error("haccsr_map2_setup: null argument"); return 1; }
+  int mx = nglt[0] > nglt[1] ? nglt[0] : nglt[1];
+  if (nglt[2] > mx) mx = nglt[2];
+  for (int k = 0; k < 3; ++k) {
+    out->tree_lo[k] = 0.0f;
+    out->tree_hi[k] = (float)(1.0 * mx);                              // Particles.cxx:1214-1215
+    out->force_lo[k] = edge;                                          // :1219-1221
+    out->force_hi[k] = (float)(1.0 * nglt[k] - (double)edge);         // :1222-1224 (double arithmetic, stored in POSVEL_T)
+  }
+  const float divscal = gpscal * gpscal * gpscal;                     // :1231 (float products)
+  const float pi = (float)(4.0 * (double)atanf(1.0f));                // :1232 (POSVEL_T pi)
+  out->fcoeff = (float)((double)divscal / 4.0 / (double)pi * fscal * tau * step_fraction);     // :1233
+  return 0;
+}
+
+float haccsr_map1_factor(float pp, float tau, float adot, float alpha) {
+  const float pf = powf(pp, (float)(1.0 + 1.0 / (double)alpha));                       // Particles.cxx:745
+  const float prefactor = (float)(1.0 / (double)(alpha * adot * pf));                  // :746 (float product, double division)
+  return prefactor * tau;                                                              // :752 (float)
+}
+
+int haccsr_particles_subcycle(haccsr_ctx *c, int nsub, const int32_t nglt[3], float edge, float gpscal, float alpha, double pp,
+                              double adot, double tau, double tau2, double fscal, float theta, int64_t ppn, int tdpts,
+                              haccsr_stats *stats) {
+  if (!c) { set_error("null context"); return 1; }
+  if (nsub < 1 || !nglt) { set_error("haccsr_particles_subcycle: bad argument"); return 1; }
+  const double step_fraction = 1.0 / nsub;                                              // Particles.cxx:1180
+  haccsr_map2 m;
+  HSR_TRY(haccsr_map2_setup(nglt, edge, gpscal, fscal, tau, step_fraction, &m));
+  // map1(gts->pp(), stepFraction*gts->tau2(), gts->adot()): the three arguments are converted to float at the call (:1186)
+  const float pt = haccsr_map1_factor((float)pp, (float)(step_fraction * tau2), (float)adot, alpha);
+  const float box_hi[3] = {(float)nglt[0], (float)nglt[1], (float)nglt[2]};
+  return haccsr_subcycle(c, nsub, pt, box_hi, m.tree_lo, m.tree_hi, m.force_lo, m.force_hi, theta, ppn, tdpts, m.fcoeff, stats);
+}
+
 int haccsr_get_tree(haccsr_ctx *c, int64_t cap, int64_t *nodes, int32_t *count, int32_t *offset, int32_t *cl,
                     int32_t *cr, float *box10) {
   if (!c) { set_error("null context"); return 1; }
@@ -536,6 +581,7 @@ int haccsr_get_tree(haccsr_ctx *c, int64_t cap, int64_t *nodes, int32_t *count, 
   if (cap < c->n_nodes) { set_error("haccsr_get_tree: cap %lld < nodes %d", (long long)cap, c->n_nodes); return 1; }
   Node *h = (Node *)malloc((size_t)c->n_nodes * sizeof(Node));
   if (!h) { set_error("out of host memory"); return 2; }
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) { free(h); set_error("haccsr_get_tree: stream synchronisation failed"); return 2; }
   cudaError_t e = cudaMemcpy(h, c->nodes.p, (size_t)c->n_nodes * sizeof(Node), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { free(h); set_error("cudaMemcpy nodes: %s", cudaGetErrorString(e)); return 2; }
   for (int i = 0; i < c->n_nodes; ++i) {

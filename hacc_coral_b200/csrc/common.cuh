@@ -113,6 +113,8 @@ struct haccsr_ctx {
   int sm_count = 0;
   int64_t cap = 0;       // particle capacity
   int64_t n_resident = 0;
+  uint64_t order_epoch = 0;   // bumped by everything that moves particles to other indices (upload, tree build, compaction, append)
+  uint64_t refresh_epoch = 0; // order_epoch when haccsr_refresh_begin made its candidate list
   haccsr::Soa cur{}, alt{};
   haccsr::ForceLawParams law{};
   bool law_set = false;
@@ -171,6 +173,10 @@ struct haccsr_ctx {
   int refresh_slot_of_dir[27] = {0};
   int64_t refresh_count[27] = {0};
   haccsr::DevBuf<int> refresh_slots;
+  haccsr::DevBuf<unsigned> refresh_cand;     // candidate indices (own buffer: a kick between begin and pack must not disturb it)
+  long long *d_slotcount = nullptr;          // 32 message sizes (device)
+  haccsr::DevBuf<unsigned char> xchg_send, xchg_recv;   // haccsr_refresh: packed messages out / in
+  haccsr::DevBuf<long long> xchg_table;      // haccsr_refresh: gathered count table, append table
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_up2 = nullptr, ev_built = nullptr, ev_main = nullptr;
   bool wait_up2 = false;    // build_tree must wait for ev_up2 before it permutes the payload arrays
@@ -199,6 +205,8 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
 int issue_host_out(haccsr_ctx *c);
 // api.cu: stable two-way partition of the ten arrays by a 0/1 flag
 int compact_by_flags(haccsr_ctx *c, const unsigned *flag, unsigned *pref, int64_t n, int64_t *n_kept);
+// refresh.cu: write the 26 messages into a device buffer, stream-ordered (no synchronisation)
+int refresh_pack_async(haccsr_ctx *c, const int64_t byte_off_by_slot[27], void *sendbuf_device);
 // scan utility (tree_build.cu): exclusive scan of n unsigned values; total written to *d_total (device).
 int scan_exclusive(haccsr_ctx *c, const unsigned *in, unsigned *out, int64_t n, unsigned long long *d_total);
 }  // namespace haccsr

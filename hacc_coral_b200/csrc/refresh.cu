@@ -106,6 +106,14 @@ __global__ void __launch_bounds__(RT) k_dir_count(const float *__restrict__ x, c
   if (t < 27 && t != 13) tilecount[(size_t)slot_of_dir[t] * ntiles + blockIdx.x] = s_cnt[t];
 }
 
+__global__ void k_slot_counts(const unsigned *__restrict__ tilebase, int ntiles, const unsigned long long *__restrict__ total,
+                              long long *__restrict__ out) {
+  const int sl = threadIdx.x;
+  if (sl >= 26) return;
+  const long long b = tilebase[(size_t)sl * ntiles], nx = (sl == 25) ? (long long)*total : (long long)tilebase[(size_t)(sl + 1) * ntiles];
+  out[sl] = nx - b;
+}
+
 struct PackLayout {
   long long byte_off[27];   // per SLOT: start of the message in the send buffer
   long long count[27];      // per SLOT: particles in the message
@@ -185,6 +193,27 @@ static RefreshGeom make_geom(const float alo[3], const float ahi[3], float ol) {
   return G;
 }
 
+int refresh_pack_async(haccsr_ctx *c, const int64_t byte_off_by_slot[27], void *sendbuf_device) {
+  if (!c) { set_error("null context"); return 1; }
+  if (!byte_off_by_slot) { set_error("haccsr_refresh_pack: null argument"); return 1; }
+  if (c->refresh_epoch != c->order_epoch) {
+    set_error("haccsr_refresh_pack: the particles were reordered (kick, upload, compaction or append) since haccsr_refresh_begin; "
+              "its candidate list no longer describes them");
+    return 1;
+  }
+  if (c->refresh_m == 0) return 0;
+  if (!sendbuf_device) { set_error("haccsr_refresh_pack: null send buffer"); return 1; }
+  HSR_CUDA(cudaSetDevice(c->device));
+  const RefreshGeom G = make_geom(c->refresh_alo, c->refresh_ahi, c->refresh_ol);
+  PackLayout L;
+  for (int sl = 0; sl < 27; ++sl) { L.byte_off[sl] = sl < 26 ? byte_off_by_slot[sl] : 0; L.count[sl] = sl < 26 ? c->refresh_count[sl] : 0; }
+  k_dir_pack<<<c->refresh_ntiles, RT, 0, c->stream>>>(c->cur, c->refresh_cand.p, (int)c->refresh_m, G, c->refresh_slots.p,
+                                                      c->refresh_ntiles, c->tilebase.p, L, (unsigned char *)sendbuf_device);
+  HSR_CUDA(cudaGetLastError());
+  return 0;     // stream-ordered
+}
+
+
 }  // namespace haccsr
 
 using namespace haccsr;
@@ -213,7 +242,7 @@ int haccsr_refresh_begin(haccsr_ctx *c, const float alive_lo[3], const float ali
   // 1. drop the ghosts: stable compaction of the alive particles to the front
   int64_t n = c->n_resident, nal = 0;
   if (n >= 0x7fffffffll) { set_error("too many particles for 32-bit indexing"); return 1; }
-  HSR_TRY(c->idxA.ensure((size_t)n + 1)); HSR_TRY(c->idxB.ensure((size_t)n + 1)); HSR_TRY(c->perm.ensure((size_t)n + 1));
+  HSR_TRY(c->idxA.ensure((size_t)n + 1)); HSR_TRY(c->idxB.ensure((size_t)n + 1)); HSR_TRY(c->refresh_cand.ensure((size_t)n + 1));
   if (n > 0) {
     k_alive_flags<<<lin_grid2(c, n), 256, 0, s>>>(c->cur.x, c->cur.y, c->cur.z, G, (long long)n, c->idxA.p);
     HSR_TRY(compact_by_flags(c, c->idxA.p, c->idxB.p, n, &nal));
@@ -226,11 +255,12 @@ int haccsr_refresh_begin(haccsr_ctx *c, const float alive_lo[3], const float ali
     k_shared_flags<<<lin_grid2(c, nal), 256, 0, s>>>(c->cur.x, c->cur.y, c->cur.z, G, (long long)nal, c->idxA.p);
     HSR_TRY(scan_exclusive(c, c->idxA.p, c->idxB.p, nal, c->d_counters + 12));
     HSR_CUDA(cudaMemcpyAsync(c->h_counters + 12, c->d_counters + 12, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    k_collect<<<lin_grid2(c, nal), 256, 0, s>>>(c->idxA.p, c->idxB.p, (long long)nal, c->perm.p);
+    k_collect<<<lin_grid2(c, nal), 256, 0, s>>>(c->idxA.p, c->idxB.p, (long long)nal, c->refresh_cand.p);
     HSR_CUDA(cudaStreamSynchronize(s));
     m = c->h_counters[12];
   }
   c->refresh_m = m;
+  c->refresh_epoch = c->order_epoch;
   c->refresh_ntiles = (int)((m + RT - 1) / RT);
   for (int k = 0; k < 3; ++k) { c->refresh_alo[k] = alive_lo[k]; c->refresh_ahi[k] = alive_hi[k]; }
   c->refresh_ol = ol;
@@ -241,38 +271,19 @@ int haccsr_refresh_begin(haccsr_ctx *c, const float alive_lo[3], const float ali
   HSR_TRY(c->tilecount.ensure((size_t)26 * nt + 1)); HSR_TRY(c->tilebase.ensure((size_t)26 * nt + 1));
   HSR_TRY(c->refresh_slots.ensure(27));
   HSR_CUDA(cudaMemcpyAsync(c->refresh_slots.p, c->refresh_slot_of_dir, 27 * sizeof(int), cudaMemcpyHostToDevice, s));
-  k_dir_count<<<nt, RT, 0, s>>>(c->cur.x, c->cur.y, c->cur.z, c->perm.p, (int)m, G, c->refresh_slots.p, nt, c->tilecount.p);
+  k_dir_count<<<nt, RT, 0, s>>>(c->cur.x, c->cur.y, c->cur.z, c->refresh_cand.p, (int)m, G, c->refresh_slots.p, nt, c->tilecount.p);
   HSR_TRY(scan_exclusive(c, c->tilecount.p, c->tilebase.p, (int64_t)26 * nt, c->d_counters + 13));
-  // message sizes = differences of the scan at slot boundaries
-  unsigned *h = (unsigned *)malloc((size_t)(26 * nt) * sizeof(unsigned));
-  if (!h) { set_error("out of host memory"); return 2; }
-  cudaError_t e = cudaMemcpyAsync(h, c->tilebase.p, (size_t)(26 * nt) * sizeof(unsigned), cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_counters + 13, c->d_counters + 13, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  if (e != cudaSuccess) { free(h); set_error("refresh count read-back failed: %s", cudaGetErrorString(e)); return 2; }
-  const long long total = c->h_counters[13];
-  for (int sl = 0; sl < 26; ++sl) {
-    const long long b = h[(size_t)sl * nt], nx = (sl == 25) ? total : (long long)h[(size_t)(sl + 1) * nt];
-    counts_by_slot[sl] = nx - b;
-    c->refresh_count[sl] = nx - b;
-  }
-  free(h);
+  // message sizes = differences of the scan at slot boundaries (26 values, read back through pinned memory)
+  k_slot_counts<<<1, 32, 0, s>>>(c->tilebase.p, nt, c->d_counters + 13, c->d_slotcount);
+  HSR_CUDA(cudaMemcpyAsync(c->h_counters, c->d_slotcount, 26 * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  HSR_CUDA(cudaStreamSynchronize(s));
+  for (int sl = 0; sl < 26; ++sl) { counts_by_slot[sl] = c->h_counters[sl]; c->refresh_count[sl] = c->h_counters[sl]; }
   return 0;
 }
 
 int haccsr_refresh_pack(haccsr_ctx *c, const int64_t byte_off_by_slot[27], void *sendbuf_device) {
-  if (!c) { set_error("null context"); return 1; }
-  if (!byte_off_by_slot) { set_error("haccsr_refresh_pack: null argument"); return 1; }
-  if (c->refresh_m == 0) return 0;
-  if (!sendbuf_device) { set_error("haccsr_refresh_pack: null send buffer"); return 1; }
-  HSR_CUDA(cudaSetDevice(c->device));
-  const RefreshGeom G = make_geom(c->refresh_alo, c->refresh_ahi, c->refresh_ol);
-  PackLayout L;
-  for (int sl = 0; sl < 27; ++sl) { L.byte_off[sl] = sl < 26 ? byte_off_by_slot[sl] : 0; L.count[sl] = sl < 26 ? c->refresh_count[sl] : 0; }
-  k_dir_pack<<<c->refresh_ntiles, RT, 0, c->stream>>>(c->cur, c->perm.p, (int)c->refresh_m, G, c->refresh_slots.p,
-                                                      c->refresh_ntiles, c->tilebase.p, L, (unsigned char *)sendbuf_device);
-  HSR_CUDA(cudaGetLastError());
-  HSR_CUDA(cudaStreamSynchronize(c->stream));
+  HSR_TRY(refresh_pack_async(c, byte_off_by_slot, sendbuf_device));
+  if (c && c->refresh_m) HSR_CUDA(cudaStreamSynchronize(c->stream));     // the caller's transport may run on any stream
   return 0;
 }
 
@@ -291,7 +302,7 @@ int haccsr_refresh_append(haccsr_ctx *c, const void *message_device, int64_t n) 
   HSR_CUDA(cudaGetLastError());
   HSR_CUDA(cudaStreamSynchronize(c->stream));
   c->n_resident += n;
-  return 0;
+  return 0;      // appended particles take new indices; the alive ones keep theirs, so a begin / pack pair stays valid
 }
 
 }  // extern "C"

@@ -1177,6 +1177,7 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
       HSR_CUDA(cudaMemcpyAsync(b.mask + n, a.mask + n, m * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
     }
     Soa tmp = c->cur; c->cur = c->alt; c->alt = tmp;
+    c->order_epoch++;
     return 0;
   }
   set_error("tree build did not converge on a node pool size");

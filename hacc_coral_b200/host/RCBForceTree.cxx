@@ -17,6 +17,8 @@ struct Shared {
   int64_t cap = 0;
   int device = -1;
   int arith = -1;     // HACCSR_ARITH_*; -1 = $HACCSR_ARITH ("x86" / "fused") or the library default
+  int cull = -1;      // warp-level culling; -1 = $HACCSR_CULL or off
+  int rank = -1;      // -1 = $HACCSR_RANK or 0
 };
 Shared &shared() { static Shared s; return s; }
 
@@ -48,6 +50,8 @@ haccsr_ctx *context_for(int64_t count) {
 
 void haccsr_facade_set_device(int device) { shared().device = device; }
 void haccsr_facade_set_arithmetic(int mode) { shared().arith = mode; }
+void haccsr_facade_set_culling(int on) { shared().cull = on ? 1 : 0; }
+void haccsr_facade_set_rank(int rank) { shared().rank = rank; }
 
 void haccsr_facade_release() {
   Shared &s = shared();
@@ -70,13 +74,19 @@ RCBForceTree<TDPTS>::RCBForceTree(POSVEL_T *minLoc, POSVEL_T *maxLoc, POSVEL_T *
                                   ID_T count, POSVEL_T *xLoc, POSVEL_T *yLoc, POSVEL_T *zLoc, POSVEL_T *xVel,
                                   POSVEL_T *yVel, POSVEL_T *zVel, POSVEL_T *mass, POSVEL_T *phiLoc, ID_T *idLoc,
                                   MASK_T *maskLoc, POSVEL_T /*avgMass*/, POSVEL_T fsm, POSVEL_T r, POSVEL_T oa, ID_T nd,
-                                  ID_T /*ds*/, ID_T /*tmin*/, ForceLaw *fl, float fcoeff, POSVEL_T /*ppc*/)
+                                  ID_T /*ds*/, ID_T /*tmin*/, ForceLaw *fl, float fcoeff, POSVEL_T ppc)
     : particleCount(count) {
   static_assert(sizeof(POSVEL_T) == 4 && sizeof(ID_T) == 8 && sizeof(MASK_T) == 2,
                 "libhaccsr is built for the reference's -DID_64 -DPOSVEL_32 types (include.mk:4)");
   memset(&m_stats, 0, sizeof(m_stats));
   Shared &s = shared();
   std::lock_guard<std::mutex> lock(s.mu);      // the reference constructor is not re-entrant either
+  // the pseudo-particle contraction of the quadrupole tree is the reference's default 0.9 on the device (tree_build.cu pp_tdr;
+  // no shipped call site passes anything else, Particles.cxx:1341-1366); another value would silently change tdr and the masses
+  if (TDPTS != 1 && ppc != 0.9f) {
+    fprintf(stderr, "RCBForceTree (libhaccsr facade): ppContract = %g is not supported (the device uses the reference's default 0.9)\n", ppc);
+    abort();
+  }
   haccsr_ctx *ctx = context_for(count);
 
   // the force law: fl == NULL means Newton with fcoeff = 1 (RCBForceTree.cxx:395-404)
@@ -103,12 +113,17 @@ RCBForceTree<TDPTS>::RCBForceTree(POSVEL_T *minLoc, POSVEL_T *maxLoc, POSVEL_T *
   int arith = s.arith;
   if (arith < 0) { const char *e = getenv("HACCSR_ARITH"); arith = (e && !strcmp(e, "x86")) ? HACCSR_ARITH_X86 : HACCSR_ARITH_FUSED; }
   if (haccsr_set_arithmetic(ctx, arith) != 0) die("haccsr_set_arithmetic");
+  int cull = s.cull;
+  if (cull < 0) { const char *e = getenv("HACCSR_CULL"); cull = (e && atoi(e) != 0) ? 1 : 0; }
+  if (haccsr_set_culling(ctx, cull) != 0) die("haccsr_set_culling");
 
   // upload -> tree build, lists, force kernel, kick -> download, transfers overlapped with the kernels
   if (haccsr_kick_host(ctx, count, xLoc, yLoc, zLoc, xVel, yVel, zVel, mass, phiLoc, idLoc, maskLoc, minLoc, maxLoc,
                        minForceLoc, maxForceLoc, oa, nd, TDPTS, fcoeff, nullptr, &m_stats) != 0)
     die("haccsr_kick_host");
-  if (!getenv("HACCSR_QUIET")) printStats(1e-3 * m_stats.ms_build);
+  int rank = s.rank;
+  if (rank < 0) { const char *e = getenv("HACCSR_RANK"); rank = e ? atoi(e) : 0; }
+  if (rank == 0 && !getenv("HACCSR_QUIET")) printStats(1e-3 * m_stats.ms_build);     // rank 0 only (RCBForceTree.cxx:503)
 }
 
 template <int TDPTS>

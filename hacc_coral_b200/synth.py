@@ -146,15 +146,20 @@ def zeldovich(ns, z=50.0, seed=5009888, ghost=11, growth_boost=1.0, dtype=np.flo
 
 def zeldovich_torch(ns, z=50.0, seed=5009888, ghost=11, growth_boost=1.0, device="cuda", return_tensor=False):
     """Same recipe as zeldovich() evaluated with torch FFTs on `device` (used by bench.py so that a
-    256^3 snapshot takes seconds).  Returns the usual dict of numpy arrays (host)."""
+    256^3 snapshot takes seconds).  Returns the usual dict of numpy arrays (host).  `ns` may be a triple (nx, ny, nz):
+    a periodic box of nx x ny x nz particles at the same spacing (the global box of a 2x1x1 or 2x2x1 decomposition of
+    equal sub-volumes); only with return_tensor."""
     import torch
     c = COSMO
-    L = ns * c["spacing"]
-    kf = 2.0 * np.pi / L
+    shape = (int(ns),) * 3 if np.isscalar(ns) else tuple(int(t) for t in ns)
+    assert return_tensor or shape[0] == shape[1] == shape[2]
     dev = torch.device(device)
-    k1 = torch.fft.fftfreq(ns, d=1.0 / ns, device=dev, dtype=torch.float64) * kf
-    kz = torch.fft.rfftfreq(ns, d=1.0 / ns, device=dev, dtype=torch.float64) * kf
-    KX, KY, KZ = torch.meshgrid(k1, k1, kz, indexing="ij")
+    ks = []
+    for ax in range(3):
+        L = shape[ax] * c["spacing"]
+        f = torch.fft.rfftfreq if ax == 2 else torch.fft.fftfreq
+        ks.append(f(shape[ax], d=1.0 / shape[ax], device=dev, dtype=torch.float64) * (2.0 * np.pi / L))
+    KX, KY, KZ = torch.meshgrid(ks[0], ks[1], ks[2], indexing="ij")
     K2 = KX ** 2 + KY ** 2 + KZ ** 2
     kt, Tt = load_transfer()
     K = torch.sqrt(K2).clamp_min(float(kt[0]))
@@ -174,22 +179,24 @@ def zeldovich_torch(ns, z=50.0, seed=5009888, ghost=11, growth_boost=1.0, device
     A = c["sigma8"] ** 2 / s2
     gen = torch.Generator(device=dev)
     gen.manual_seed(int(seed))
-    white = torch.randn((ns, ns, ns), generator=gen, device=dev, dtype=torch.float64)
-    dk = torch.fft.rfftn(white) * torch.sqrt(A * P * float(ns) ** 3 / L ** 3)
+    white = torch.randn(shape, generator=gen, device=dev, dtype=torch.float64)
+    # particles per volume: N / V = spacing^-3 whatever the shape of the box
+    dk = torch.fft.rfftn(white) * torch.sqrt(A * P / c["spacing"] ** 3)
     del white
     om = c["omega_dm"] + c["omega_b"]
     D = _growth(1.0 / (1.0 + z), om, 1.0 - om) * growth_boost
     invk2 = torch.where(K2 > 0, 1.0 / K2.clamp_min(1e-300), torch.zeros_like(K2))
-    g = torch.arange(ns, device=dev, dtype=torch.float64) + 0.5
     pos = []
     for ax, Kc in enumerate((KX, KY, KZ)):
-        psi = torch.fft.irfftn(1j * Kc * dk * invk2, s=(ns, ns, ns))
-        shape = [1, 1, 1]
-        shape[ax] = ns
-        pos.append(torch.remainder(g.reshape(shape) + D * psi / c["spacing"], ns).reshape(-1))
+        psi = torch.fft.irfftn(1j * Kc * dk * invk2, s=shape)
+        sh = [1, 1, 1]
+        sh[ax] = shape[ax]
+        g = torch.arange(shape[ax], device=dev, dtype=torch.float64) + 0.5
+        pos.append(torch.remainder(g.reshape(sh) + D * psi / c["spacing"], shape[ax]).reshape(-1))
     pos = torch.stack(pos, dim=1)
-    if return_tensor:          # (ns^3, 3) float64 positions in [0, ns) on `device`, no ghost shell
+    if return_tensor:          # (nx*ny*nz, 3) float64 positions in [0, n_axis) on `device`, no ghost shell
         return pos
+    ns = shape[0]
     if ghost > 0:
         out = []
         for sx in (-1, 0, 1):

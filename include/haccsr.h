@@ -185,6 +185,30 @@ int haccsr_subcycle(haccsr_ctx *ctx, int nsub, float prefactor_tau, const float 
                     const float tree_hi[3], const float force_lo[3], const float force_hi[3], float theta,
                     int64_t ppn, int tdpts, float fcoeff, haccsr_stats *stats);
 
+/* ---- the glue of Particles::map2 / map1 / subCycle as code (host arithmetic only; usable without a GPU) -------------------------
+ * haccsr_map2_setup computes what Particles::map2 hands to the tree (src/cpu/Particles.cxx:1205-1233), with the reference's own
+ * promotions (float members, double literals and TimeStepper values, pi = 4.0*atanf(1.0) stored in a float):
+ *   tree box   [0, max(nglt)]^3                                   (:1213-1216)
+ *   force box  [edge, nglt - edge] per dimension                    (:1219-1228)
+ *   fcoeff     c = gpscal^3 / 4.0 / pi * fscal * tau * step_fraction  (:1230-1233)
+ * nglt = Domain::ng_local_total, edge = m_edge, gpscal = m_gpscal = float(ng) / float(np) (:152-153), fscal / tau =
+ * TimeStepper::fscal() / tau() (double), step_fraction = 1.0 / nsub (:1180). */
+typedef struct haccsr_map2 {
+  float tree_lo[3], tree_hi[3], force_lo[3], force_hi[3];
+  float fcoeff;
+} haccsr_map2;
+int haccsr_map2_setup(const int32_t nglt[3], float edge, float gpscal, double fscal, double tau, double step_fraction,
+                      haccsr_map2 *out);
+/* The factor Particles::map1 multiplies the velocities with, prefactor * tau in float (src/cpu/Particles.cxx:745-754):
+ * pf = powf(pp, 1.0 + 1.0 / alpha), prefactor = 1.0 / (alpha * adot * pf); map1's arguments pp, tau, adot are floats. */
+float haccsr_map1_factor(float pp, float tau, float adot, float alpha);
+/* Particles::subCycle(gts) on the resident particles from the TimeStepper's scalars alone (src/cpu/Particles.cxx:1176-1201):
+ * step_fraction = 1.0 / nsub; nsub x [ map1(pp, step_fraction * tau2, adot) ; map2(gts, step_fraction) ; map1(...) ] with the
+ * boxes and c of haccsr_map2_setup.  The force law, rmax and rsm are those of haccsr_set_force_law (m_fl, m_fsrrmax, m_rsm). */
+int haccsr_particles_subcycle(haccsr_ctx *ctx, int nsub, const int32_t nglt[3], float edge, float gpscal, float alpha,
+                              double pp, double adot, double tau, double tau2, double fscal, float theta, int64_t ppn,
+                              int tdpts, haccsr_stats *stats);
+
 /* ---- PM coupling: the particle side of the long-range step -------------------------------------
  * The FFT Poisson solver stays the reference's; these two calls replace the particle loops either side of it so the
  * particles need not leave the GPU between sub-cycles.  Grids are ng[0]*ng[1]*ng[2] floats, index (ix*ng[1]+iy)*ng[2]+iz
@@ -226,6 +250,32 @@ int haccsr_refresh_pack(haccsr_ctx *ctx, const int64_t byte_off_by_slot[27], voi
 int haccsr_refresh_append(haccsr_ctx *ctx, const void *message_device, int64_t n);
 /* Number of particles currently resident in the context. */
 int64_t haccsr_resident(haccsr_ctx *ctx);
+
+/* ---- overload refresh as one call, transport included (what a C++ HACC rank calls at a refresh step) ------------------------
+ * haccsr_refresh = haccsr_refresh_begin + plan + haccsr_refresh_pack + one grouped ncclSend/ncclRecv over NVLink + append.
+ * Replaces: MC3Extras::refreshParticles -> ParticleExchange::exchangeParticles (src/simulation/MC3Extras.cxx:660-706,
+ * src/halo_finder/ParticleExchange.cxx:488-762) for the particles resident in the context.  The ranks form the periodic
+ * Cartesian grid dims[0] x dims[1] x dims[2] of Partition (src/halo_finder/Partition.cxx:121-137): rank = (px*dims[1] + py)*
+ * dims[2] + pz, and nccl_comm is an ncclComm_t over exactly those ranks in that order (NULL is allowed for 1 x 1 x 1, where
+ * every neighbour is the rank itself).  Collective: every rank of the communicator must call it.  On return the context
+ * holds its alive particles (stable order) followed by the received ghosts in (source rank, direction) order --
+ * deterministic, and bit-identical to extracting each rank's overloaded sub-volume from the global particle set.
+ * NCCL is loaded at run time (libnccl.so.2); status 3 if it cannot be. */
+typedef struct haccsr_refresh_stats {
+  int64_t alive, ghosts, sent;             /* particles kept, received, sent (a particle goes to up to 7 neighbours)       */
+  int64_t bytes_sent, bytes_received;      /* packed message bytes, self messages included                                 */
+  int64_t bytes_sent_remote;               /* bytes that crossed NVLink (bytes_sent minus the messages to the rank itself) */
+  int32_t messages_received, reserved;
+  float ms_total;                          /* device time of the whole call (events on the context's stream)               */
+} haccsr_refresh_stats;
+int haccsr_refresh(haccsr_ctx *ctx, void *nccl_comm, const int32_t dims[3], int32_t rank, const float alive_lo[3],
+                   const float alive_hi[3], float ol, haccsr_refresh_stats *stats);
+/* Communicator helpers for hosts that do not link NCCL themselves: rank 0 obtains an id, distributes its 128 bytes by its own
+ * means (MPI_Bcast in HACC; torch.distributed in bench.py), every rank creates its communicator on its device. */
+#define HACCSR_NCCL_ID_BYTES 128
+int haccsr_nccl_unique_id(void *id128);
+int haccsr_nccl_comm_create(void **comm, int device, int nranks, int rank, const void *id128);
+int haccsr_nccl_comm_destroy(void *comm);
 
 /* ---- inspection (tests and tools): the tree and the lists of the last kick ---------------------- */
 /* Node table, `cap` entries per array; box10 = xmin[3] xmax[3] xc[3] ppm per node

@@ -30,5 +30,12 @@ g++ $FL -c "$HERE/ref_harness.cxx" -o "$OUT/obj/ref_harness.o"
 COMMON="$OUT/obj/ForceLaw.o $OUT/obj/partition_stub.o $OUT/obj/BGQCM.o $OUT/obj/bigchunk.o $OUT/obj/ref_harness.o"
 g++ -shared -fopenmp -o "$OUT/libhaccref.so" "$OUT/obj/RCBForceTree.o" $COMMON -lrt -lpthread
 g++ -shared -fopenmp -o "$OUT/libhaccref_vmax.so" "$OUT/obj/RCBForceTree_vmax.o" $COMMON -lrt -lpthread
+# libhaccref_cic.so: the reference's own cloud-in-cell loops (src/cpu/Particles.cxx: array_index, cic, inverse_cic).  The file
+# as a whole needs MPI; the three function bodies are cut out of it *in a pipe* between our scaffolding (stubs/cic_pre.h,
+# stubs/cic_post.cxx) -- again no reference text is written anywhere.
+PX="$REF/src/cpu/Particles.cxx"
+fn() { awk -v start="$1" '$0 ~ start {f=1} f {print} f && /^}/ {exit}' "$PX"; }
+{ cat "$HERE/stubs/cic_pre.h"; fn '^inline int *$'; fn '^void Particles::cic\\(\\) \\{'; fn '^void Particles::inverse_cic\\('; cat "$HERE/stubs/cic_post.cxx"; } | \
+  g++ -O3 -fopenmp -fPIC -w -x c++ -shared - -o "$OUT/libhaccref_cic.so"
 rm -rf "$OUT/obj"
-echo "built $OUT/libhaccref.so $OUT/libhaccref_vmax.so"
+echo "built $OUT/libhaccref.so $OUT/libhaccref_vmax.so $OUT/libhaccref_cic.so"

@@ -126,3 +126,43 @@ def rcb_kick(p, tree_lo, tree_hi, force_lo, force_hi, rsm, theta, ppn, fcoeff=1.
             tree["tdr"], tree["ppm12"] = pp[:, 0], pp[:, 1:]
     lib.ref_set_tdpts(1)
     return q, stats, tree
+
+
+# ---- the reference's cloud-in-cell loops (oracle/_ref/libhaccref_cic.so: src/cpu/Particles.cxx array_index, cic, inverse_cic) ----
+_cic = None
+
+
+def cic_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libhaccref_cic.so"))
+
+
+def _cic_lib():
+    global _cic
+    if _cic is None:
+        lib = C.CDLL(os.path.join(_HERE, "_ref", "libhaccref_cic.so"))
+        fp, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        lib.ref_cic.argtypes = [C.c_int64, fp, fp, fp, i32p, C.c_float, fp]
+        lib.ref_inverse_cic.argtypes = [C.c_int64] + [fp] * 7 + [i32p, fp, C.c_float, C.c_float, C.c_int]
+        _cic = lib
+    return _cic
+
+
+def cic(p, ng, gpscal):
+    """Particles::cic of the reference on particle dict p: returns the (ng0, ng1, ng2) float32 grid; the deposit weight is
+    c = gpscal^3 formed in float as the reference does (Particles.cxx:605)."""
+    x, y, z = (np.ascontiguousarray(p[k], dtype=np.float32).copy() for k in ("x", "y", "z"))
+    ng3 = np.asarray(ng, dtype=np.int32)
+    rho = np.zeros(int(np.prod(ng3)) + 1, dtype=np.float32)
+    assert _cic_lib().ref_cic(x.size, _fp(x), _fp(y), _fp(z), ng3.ctypes.data_as(C.POINTER(C.c_int32)), float(gpscal), _fp(rho)) == 0
+    return rho[:-1].reshape(tuple(int(t) for t in ng3))
+
+
+def inverse_cic(p, grid, tau, fscal, comp):
+    """Particles::inverse_cic(tau, fscal, comp) of the reference: returns the updated array (vx, vy, vz or phi for comp 0..3)."""
+    a = {k: np.ascontiguousarray(p[k], dtype=np.float32).copy() for k in ("x", "y", "z", "vx", "vy", "vz", "phi")}
+    grid = np.ascontiguousarray(grid, dtype=np.float32)
+    ng3 = np.asarray(grid.shape, dtype=np.int32)
+    g = np.concatenate([grid.ravel(), np.zeros(1, np.float32)])
+    assert _cic_lib().ref_inverse_cic(a["x"].size, *[_fp(a[k]) for k in ("x", "y", "z", "vx", "vy", "vz", "phi")],
+                                      ng3.ctypes.data_as(C.POINTER(C.c_int32)), _fp(g), float(tau), float(fscal), int(comp)) == 0
+    return a[("vx", "vy", "vz", "phi")[comp]]

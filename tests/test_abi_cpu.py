@@ -109,3 +109,45 @@ class Particles {
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"),
                         "-I", os.path.join(ROOT, "hacc_coral_b200", "host"), str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_map2_glue_matches_the_reference_expressions():
+    """haccsr_map2_setup / haccsr_map1_factor against the expressions of Particles::map2 (reference src/cpu/Particles.cxx:
+    1213-1233) and Particles::map1 (:745-754) re-evaluated here with numpy under C's promotion rules, and against values
+    worked out by hand for the shipped configuration (indat: ng = np, edge 3.2, nsub 5)."""
+    import numpy as np
+    f32, f64 = np.float32, np.float64
+    # hand-computed: nglt = 151^3 (C1), edge = 3.2f, gpscal = 1, fscal = 1.5, tau = 0.1, nsub = 5
+    m = capi.map2_setup((151, 151, 151), 3.2, 1.0, 1.5, 0.1, 1.0 / 5)
+    assert m["tree_lo"] == [0.0] * 3 and m["tree_hi"] == [151.0] * 3
+    assert m["force_lo"] == [float(f32(3.2))] * 3
+    assert m["force_hi"] == [float(f32(151.0 - f64(f32(3.2))))] * 3 == [147.8000030517578] * 3
+    pi32 = f32(4.0 * f64(np.arctan(f32(1.0), dtype=f32)))
+    assert float(pi32) == 3.1415927410125732
+    assert m["fcoeff"] == float(f32(1.0 / 4.0 / f64(pi32) * 1.5 * 0.1 * 0.2)) == 0.0023873241152614355
+    # general case, non-cubic sub-volume and gpscal != 1: every intermediate in the reference's type
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        nglt = [int(t) for t in rng.integers(20, 400, 3)]
+        edge, gp = f32(rng.uniform(1, 5)), f32(rng.uniform(0.5, 2.0))
+        fscal, tau, sf = rng.uniform(0.5, 3), rng.uniform(0.01, 0.2), 1.0 / int(rng.integers(1, 9))
+        m = capi.map2_setup(nglt, float(edge), float(gp), fscal, tau, sf)
+        assert m["tree_hi"] == [float(f32(1.0 * max(nglt)))] * 3
+        assert m["force_hi"] == [float(f32(1.0 * n - f64(edge))) for n in nglt]
+        divscal = f32(f32(gp * gp) * gp)
+        assert m["fcoeff"] == float(f32(f64(divscal) / 4.0 / f64(pi32) * fscal * tau * sf))
+        pp, t1, adot, alpha = f32(rng.uniform(0.1, 1)), f32(rng.uniform(0.001, 0.1)), f32(rng.uniform(0.5, 2)), f32(1.0)
+        got = capi.map1_factor(float(pp), float(t1), float(adot), float(alpha))
+        pf = f32(np.power(pp, f32(1.0 + 1.0 / f64(alpha)), dtype=f32))
+        want = f32(f32(1.0 / f64(f32(f32(alpha * adot) * pf))) * t1)
+        assert abs(got - float(want)) <= 2e-7 * abs(float(want))     # powf of libm vs numpy: last-bit differences only
+
+
+def test_refresh_stats_struct_layout_matches_header():
+    src = open(os.path.join(ROOT, "include", "haccsr.h")).read()
+    body = re.search(r"typedef struct haccsr_refresh_stats \{(.*?)\} haccsr_refresh_stats;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in re.findall(r"\b(?:int64_t|int32_t|float)\s+([a-z_, ]+);", body):
+        fields += [t.strip() for t in decl.split(",")]
+    assert fields == [f for f, _ in capi.RefreshStats._fields_]

@@ -1,6 +1,8 @@
 """CPU tests of the CIC restatement (oracle/haccsr_oracle.c: orc_cic, orc_inverse_cic; reference src/cpu/Particles.cxx:589-714).
-The reference's Particles.cxx cannot be compiled here (MPI), so the restatement is pinned by properties that any correct
-cloud-in-cell pair has, and by an independent float64 numpy evaluation of the same weights."""
+PINNED: bit-for-bit equal to the reference's own loops -- Particles::array_index / cic / inverse_cic cut out of Particles.cxx and
+compiled by oracle/build_ref.sh into oracle/_ref/libhaccref_cic.so (the file as a whole needs MPI, the three functions do not) --
+through the committed fixture tests/golden/ref_cic_clustered12k.npz (tests/golden/make_golden_cic.py) and, where the compiled
+reference is present, live.  Plus properties any correct cloud-in-cell pair has and an independent float64 evaluation."""
 import numpy as np
 import pytest
 
@@ -96,3 +98,35 @@ def test_inverse_cic_matches_float64_and_is_adjoint_of_cic(oracle, snap):
     lhs = float((oracle.cic(snap, ng, c).astype(np.float64) * grid).sum())
     rhs = c * float(_np_interp(snap, grid).sum())
     assert abs(lhs - rhs) <= 1e-4 * abs(rhs) + 1e-3
+
+
+GOLD = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "ref_cic_clustered12k.npz")
+
+
+def load_cic_golden():
+    d = np.load(GOLD)
+    p = {k: d[k] for k in ("x", "y", "z", "vx", "vy", "vz", "phi")}
+    p["mass"] = np.ones(p["x"].size, np.float32)
+    p["id"] = np.arange(p["x"].size, dtype=np.int64)
+    p["mask"] = np.zeros(p["x"].size, np.uint16)
+    return d, p, tuple(int(t) for t in d["ng"])
+
+
+def test_oracle_cic_is_bit_equal_to_the_compiled_reference_fixture(oracle):
+    d, p, ng = load_cic_golden()
+    assert np.array_equal(oracle.cic(p, ng, float(d["c"])), d["rho"])
+    for comp, key in enumerate(("vx", "vy", "vz", "phi")):
+        assert np.array_equal(oracle.inverse_cic(p, d["grid"], float(d["tau"]), float(d["fscal"]), comp), d["out_" + key]), key
+
+
+def test_oracle_cic_is_bit_equal_to_the_compiled_reference_live(oracle, snap):
+    from oracle import refbind
+    if not refbind.cic_available():
+        pytest.skip("oracle/_ref/libhaccref_cic.so not built (no /root/reference on this box)")
+    ng = (20, 22, 21)
+    gpscal = np.float32(1.07)
+    c = np.float32(np.float32(gpscal * gpscal) * gpscal)
+    assert np.array_equal(oracle.cic(snap, ng, float(c)), refbind.cic(snap, ng, gpscal))
+    grid = np.random.default_rng(17).standard_normal(ng).astype(np.float32)
+    for comp in range(4):
+        assert np.array_equal(oracle.inverse_cic(snap, grid, 0.21, 2.3, comp), refbind.inverse_cic(snap, grid, 0.21, 2.3, comp)), comp

@@ -1,5 +1,6 @@
-"""GPU tests (-m gpu) of the PM coupling kernels (csrc/cic.cu) through the C ABI against the oracle restatement of
-Particles::cic / Particles::inverse_cic (reference src/cpu/Particles.cxx:589-714)."""
+"""GPU tests (-m gpu) of the PM coupling kernels (csrc/cic.cu) through the C ABI against the reference's own loops
+(Particles::cic / Particles::inverse_cic, reference src/cpu/Particles.cxx:589-714): the committed fixture generated from the
+compiled reference (tests/golden/ref_cic_clustered12k.npz) and the oracle restatement that is bit-equal to it."""
 import numpy as np
 import pytest
 
@@ -78,3 +79,22 @@ def test_cic_empty_and_single_particle(oracle):
     g.close()
     assert np.array_equal(rho, oracle.cic(one, ng, 2.0))
     assert abs(float(rho.sum()) - 2.0) < 1e-6 and rho[1, 2, 3] == np.float32(2.0 * 0.75 * 0.5 * 0.25)
+
+
+def test_against_the_compiled_reference_fixture():
+    """haccsr_inverse_cic bit-identical, haccsr_cic within float rounding of the reference's sequential float sum (the device
+    rounds the exact sum once: |difference| <= 1e-5 of the cell value + 1e-6)."""
+    from tests.test_cic_cpu import load_cic_golden
+    d, p, ng = load_cic_golden()
+    g = H.HaccSR(p["x"].size)
+    g.upload(p)
+    rho = g.cic(ng, float(d["c"]))
+    for comp in range(4):
+        g.inverse_cic(d["grid"], tau=float(d["tau"]), fscal=float(d["fscal"]), comp=comp)
+    out = g.download()
+    g.close()
+    for key in ("vx", "vy", "vz", "phi"):
+        assert np.array_equal(out[key], d["out_" + key]), key
+    ref = d["rho"].astype(np.float64)
+    assert np.all(np.abs(rho.astype(np.float64) - ref) <= 1e-5 * ref + 1e-6)
+    assert abs(float(rho.astype(np.float64).sum()) - float(ref.sum())) <= 1e-6 * float(ref.sum())

@@ -25,7 +25,21 @@ from tests.util import RSM, THETA, accel_errors, boxes, by_id, compare_trees
 pytestmark = pytest.mark.gpu
 
 
-ARITHS = [pytest.param(H.ARITH_FUSED, id="fused"), pytest.param(H.ARITH_X86, id="x86")]
+class Mode(int):
+    """Arithmetic mode of the pair kernel (compares equal to H.ARITH_*) plus the warp-level culling switch."""
+    cull = False
+
+
+def _mode(arith, cull):
+    m = Mode(arith)
+    m.cull = cull
+    return m
+
+
+# every kick test runs in both arithmetic modes and, for the fused mode, with warp-level culling on as well: culling only skips
+# pairs whose accumulate predicate is false in every lane, so the same gates (and bit-identical outputs) must hold
+ARITHS = [pytest.param(_mode(H.ARITH_FUSED, False), id="fused"), pytest.param(_mode(H.ARITH_X86, False), id="x86"),
+          pytest.param(_mode(H.ARITH_FUSED, True), id="fused-cull")]
 
 
 def count_form(oracle, arith):
@@ -35,8 +49,9 @@ def count_form(oracle, arith):
 
 def gpu_run(p, b, theta, ppn, coef=H.POLY5, kind=H.LAW_SR_POLY, rsm=RSM, fcoeff=1.0, want_tree=True, count=True,
             arith=H.ARITH_FUSED, tdpts=1):
-    g = H.HaccSR(max(int(p["x"].size), 1), arith=arith)
+    g = H.HaccSR(max(int(p["x"].size), 1), arith=int(arith))
     try:
+        g.set_culling(getattr(arith, "cull", False))
         g.set_force_law(kind, coef, rsm, H.RMAX)
         g.upload(p)
         st = g.kick(*b, theta, ppn, fcoeff=fcoeff, count_in_cutoff=count, tdpts=tdpts)

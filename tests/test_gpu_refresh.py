@@ -95,3 +95,66 @@ def test_refresh_then_kick_is_deterministic():
         outs.append(g.download())
         g.close()
     _same(outs[0], outs[1])
+
+
+def test_c_abi_refresh_single_rank():
+    """haccsr_refresh (plan, pack, exchange, append in one C call) on a 1 x 1 x 1 decomposition: every neighbour is the rank
+    itself, so all 26 messages take the device-local path (ParticleExchange.cxx:676-695); no communicator needed."""
+    dims = (1, 1, 1)
+    pos, vel = U.global_particles(dims, EXT, 60000, seed=11)
+    dec = Decomposition(dims, 0)
+    p = U.rank_particles(pos, vel, dims, dec.pos, EXT, OL, seed=0)
+    want = RO.refresh_all([p], [dec], ALO, AHI, OL)[0]
+    g = H.HaccSR(int(want["x"].size) + 1000)
+    g.upload(p)
+    info = g.refresh(None, dims, 0, ALO, AHI, OL)
+    out = g.download()
+    assert info["alive"] == 60000 and info["ghosts"] == want["x"].size - 60000 and g.resident() == want["x"].size
+    assert info["bytes_sent_remote"] == 0 and info["bytes_sent"] == info["bytes_received"] and info["ms_total"] > 0
+    _same(out, want)
+    info2 = g.refresh(None, dims, 0, ALO, AHI, OL)      # idempotent
+    out2 = g.download()
+    g.close()
+    assert {k: v for k, v in info2.items() if k != "ms_total"} == {k: v for k, v in info.items() if k != "ms_total"}
+    _same(out2, want)
+
+
+def test_c_abi_refresh_rejects_bad_arguments():
+    g = H.HaccSR(1000)
+    with pytest.raises(H.HaccSRError):
+        g.refresh(None, (2, 1, 1), 0, ALO, AHI, OL)          # two ranks need a communicator
+    with pytest.raises(H.HaccSRError):
+        g.refresh(None, (1, 1, 1), 3, ALO, AHI, OL)          # rank outside the decomposition
+    g.close()
+
+
+def test_kick_between_begin_and_pack_is_refused():
+    """The candidate list of haccsr_refresh_begin indexes the particles as they lay at that moment (it lives in its own
+    buffer, not in the build's scratch); a kick in between permutes them, and haccsr_refresh_pack refuses to pack stale
+    indices instead of writing the wrong particles."""
+    import torch
+    dims = (1, 1, 1)
+    pos, vel = U.global_particles(dims, EXT, 20000, seed=12)
+    dec = Decomposition(dims, 0)
+    p = U.rank_particles(pos, vel, dims, dec.pos, EXT, OL, seed=0)
+    plan = RefreshPlan(dec)
+    bufs = []
+    for kick in (False, True):
+        g = H.HaccSR(60000)
+        g.set_force_law(H.LAW_SR_POLY, H.POLY5, 0.007, H.RMAX)
+        g.upload(p)
+        c, nal = g.refresh_begin(ALO, AHI, OL, plan.slot_of_dir)
+        off, _, total = plan.send_layout(c, g.refresh_message_bytes)
+        if kick:
+            side = [e + 2 * OL for e in EXT]
+            g.kick([0.0] * 3, [max(side)] * 3, [OL] * 3, [s - OL for s in side], 0.5, 64, count=nal, skip_force=True)
+        buf = torch.zeros(max(int(total), 16), dtype=torch.uint8, device="cuda")
+        if not kick:
+            g.refresh_pack(off, buf.data_ptr())
+            bufs.append(buf.cpu().numpy().copy())
+        else:
+            # after a kick the particles are in tree order: the candidate indices no longer describe them, and the library
+            # must say so instead of packing stale indices
+            with pytest.raises(H.HaccSRError):
+                g.refresh_pack(off, buf.data_ptr())
+        g.close()

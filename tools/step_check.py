@@ -7,8 +7,8 @@
 Every rank generates the same global Zel'dovich snapshot (same seed), keeps the alive particles of its sub-volume of
 HACC's 3-D decomposition (reference src/halo_finder/Partition.cxx:121-137, src/simulation/Domain.cxx:65-79) in local grid
 units, and then
-  1. rebuilds its overload (ghost) zone with hacc_coral_b200.refresh.overload_refresh -- device classify + pack, ONE
-     all-to-all-v over NCCL, device append (replaces ParticleExchange, src/halo_finder/ParticleExchange.cxx:488-762);
+  1. rebuilds its overload (ghost) zone with haccsr_refresh (C ABI) -- device classify + pack, ONE grouped
+     ncclSend/ncclRecv, device append (replaces ParticleExchange, src/halo_finder/ParticleExchange.cxx:488-762);
   2. checks the result against the ghost zone extracted directly from the global snapshot (periodic images): same
      multiset of (id, image), positions equal to float32 rounding;
   3. runs the short-range kick (tree build + lists + force kernel) on the refreshed particles and on the directly
@@ -27,24 +27,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def image_key(p, ol, ext):
-    """id * 27 + code of the periodic image the particle is (which side of the alive region, per dimension)."""
-    code = np.zeros(p["x"].size, dtype=np.int64)
-    for k, a in enumerate(("x", "y", "z")):
-        s = np.where(p[a] < np.float32(ol), 0, np.where(p[a] >= np.float32(ol + ext[k]), 2, 1))
-        code = code * 3 + s
-    return p["id"].astype(np.int64) * 27 + code
-
-
-def near_boundary(p, ol, ext, eps=1e-3):
-    """Particles within eps of a plane where float32 rounding decides membership (outer ghost faces, alive faces): the two
-    constructions may legitimately disagree on those (about one particle per face at 256^2 cells), so they are left out
-    of the set comparison."""
-    m = np.zeros(p["x"].size, dtype=bool)
-    for k, a in enumerate(("x", "y", "z")):
-        for plane in (0.0, ol, ol + ext[k], 2 * ol + ext[k]):
-            m |= np.abs(p[a].astype(np.float64) - plane) < eps
-    return m
+from tools.decomposed import CART, compare_sets, extract, image_key, make_comm   # noqa: E402
 
 
 def main():
@@ -58,74 +41,32 @@ def main():
     import torch.distributed as dist
     import hacc_coral_b200 as H
     from hacc_coral_b200 import synth
-    from hacc_coral_b200.refresh import Decomposition, overload_refresh
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dims = Decomposition.for_world(world)
-    dec = Decomposition(dims, rank)
+    dims = CART[world]
     G, ol = args.global_side, float(args.ol)
-    ext = [G // d for d in dims]
-    assert all(e * d == G for e, d in zip(ext, dims))
-    origin = np.array([dec.pos[k] * ext[k] for k in range(3)], dtype=np.float64)
-    # the global snapshot and both extractions are evaluated with torch on the GPU (134 M particles at --global-side 512)
-    dev = torch.device("cuda", local)
-    pos = synth.zeldovich_torch(G, z=args.z, seed=5009888, ghost=0, device=dev, return_tensor=True)
-    t_origin = torch.as_tensor(origin, device=dev)
-    exta = torch.as_tensor(np.asarray(ext, dtype=np.float64), device=dev)
-    ahi32 = (exta + ol).to(torch.float32)
-    ahi32m = torch.nextafter(ahi32, torch.zeros_like(ahi32))
-    top32 = torch.nextafter((exta + 2 * ol).to(torch.float32), torch.zeros_like(ahi32))
-
-    def pack(loc32, ids):
-        loc = loc32.cpu().numpy()
-        p = synth._pack(loc[:, 0], loc[:, 1], loc[:, 2])
-        p["id"] = ids.cpu().numpy().astype(np.int64)
-        return p
-
-    m = ((pos >= t_origin) & (pos < t_origin + exta)).all(dim=1)
-    alive = pack(torch.minimum((pos[m] - t_origin + ol).to(torch.float32), ahi32m), torch.nonzero(m).reshape(-1))
-    # direct extraction of alive + ghosts: every periodic image inside the alive region grown by ol, with the float32
-    # arithmetic of the exchange (the owner's local float32 coordinate shifted by a whole number of sub-volume extents,
-    # ParticleExchange.cxx:672-673,702-708), so that both constructions hold bit-identical positions
-    owner_origin = torch.floor(pos / exta) * exta
-    owner_local = torch.minimum((pos - owner_origin + ol).to(torch.float32), ahi32m)
-    pieces, ids = [], []
-    for sx in (-1, 0, 1):
-        for sy in (-1, 0, 1):
-            for sz in (-1, 0, 1):
-                shift = torch.tensor([sx, sy, sz], device=dev, dtype=torch.float64) * G
-                q = pos + shift - t_origin + ol
-                mm = ((q >= 0) & (q < exta + 2 * ol)).all(dim=1)
-                delta = (owner_origin[mm] + shift - t_origin).to(torch.float32)        # -ext, 0 or +ext per dimension
-                pieces.append(torch.minimum(owner_local[mm] + delta, top32)); ids.append(torch.nonzero(mm).reshape(-1))
-                del q, mm, delta
-    direct = pack(torch.cat(pieces), torch.cat(ids))
-    del pos, pieces, ids, owner_origin, owner_local, m
-    torch.cuda.empty_cache()
+    alive, direct, ext = extract(G, dims, rank, ol, "cuda:%d" % local, z=args.z)
+    comm = make_comm(local, world, rank, dist if world > 1 else None)
 
     alo, ahi = (ol,) * 3, tuple(ol + e for e in ext)
     cap = int(direct["x"].size * 1.05) + 4096
     g = H.HaccSR(cap, device=local)
     g.set_force_law(H.LAW_SR_POLY, H.POLY5, 0.007, H.RMAX)
     g.upload(alive)
-    overload_refresh(g, dec, alo, ahi, ol)                 # warm-up: NCCL channels, buffers (the refresh is idempotent)
+    g.refresh(comm, dims, rank, alo, ahi, ol)              # warm-up: NCCL channels, buffers (the refresh is idempotent)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    info = overload_refresh(g, dec, alo, ahi, ol)
+    info = g.refresh(comm, dims, rank, alo, ahi, ol)
     e1.record()
     torch.cuda.synchronize()
     ms_refresh = e0.elapsed_time(e1)
     got = g.download()
-    ka, kb = image_key(got, ol, ext), image_key(direct, ol, ext)
-    na, nb_ = near_boundary(got, ol, ext), near_boundary(direct, ol, ext)
-    same_set = np.setxor1d(ka[~na], kb[~nb_]).size == 0 and abs(int(ka.size) - int(kb.size)) <= 64
-    _, ia, ib = np.intersect1d(ka, kb, return_indices=True)
-    dpos = max(float(np.abs(got[a][ia].astype(np.float64) - direct[a][ib]).max()) for a in ("x", "y", "z")) if ia.size else -1.0
+    same_set, dpos, _ = compare_sets(got, direct, ol, ext)
 
     top = float(max(ext) + 2 * ol)                         # tree box [0, max(nglt)]^3 (Particles.cxx:1213-1216)
     lo, hi = [0.0] * 3, [top] * 3
