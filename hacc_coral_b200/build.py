@@ -28,13 +28,24 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     """Compile csrc/*.cu -> csrc/libhaccsr.so and host/RCBForceTree.cxx -> host/libhaccsr_facade.so."""
     out = os.path.join(CSRC, "libhaccsr.so")
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
-                                                       os.path.join(_HERE, "..", "include", "haccsr.h")]
-    if force or _stale(out, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
-        if verbose:
-            cmd += ["-Xptxas", "-v"]
-        subprocess.check_call(cmd)
+    common = [os.path.join(CSRC, "common.cuh"), os.path.join(_HERE, "..", "include", "haccsr.h")]
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    # one object per source, compiled in parallel and only when stale (force.cu alone takes minutes: 5 arithmetic variants)
+    jobs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [os.path.join(CSRC, src)] + common):
+            cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", os.path.join(CSRC, src), "-o", obj]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            jobs.append((src, subprocess.Popen(cmd)))
+    failed = [src for src, pr in jobs if pr.wait() != 0]
+    if failed:
+        raise RuntimeError("nvcc failed on " + ", ".join(failed))
+    if jobs or force or _stale(out, objs):
+        subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-ldl"])
     facade_src = os.path.join(HOST, "RCBForceTree.cxx")
     if os.path.exists(facade_src):
         fout = os.path.join(HOST, "libhaccsr_facade.so")

@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 LAW_SR_POLY, LAW_SR_FIT, LAW_SR_INTERP, LAW_NEWTON = 0, 1, 2, 3
-ARITH_FUSED, ARITH_X86 = 0, 1       # include/haccsr.h HACCSR_ARITH_*
+ARITH_FUSED, ARITH_X86, ARITH_FUSED_RS3 = 0, 1, 2       # include/haccsr.h HACCSR_ARITH_*
 # reference src/halo_finder/ForceLaw.cxx:109-114 (== BGQStep16.c:167) and :98-104
 POLY5 = np.array([0.269327, -0.0750978, 0.0114808, -0.00109313, 0.0000605491, -0.00000147177], dtype=np.float32)
 POLY6 = np.array([0.271431, -0.0783394, 0.0133122, -0.00159485, 0.000132336, -0.00000663394, 0.000000147305],

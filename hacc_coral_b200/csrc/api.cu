@@ -271,7 +271,7 @@ int haccsr_set_culling(haccsr_ctx *c, int on) {
 
 int haccsr_set_arithmetic(haccsr_ctx *c, int mode) {
   if (!c) { set_error("null context"); return 1; }
-  if (mode != HACCSR_ARITH_FUSED && mode != HACCSR_ARITH_X86) { set_error("unknown arithmetic mode %d", mode); return 1; }
+  if (mode != HACCSR_ARITH_FUSED && mode != HACCSR_ARITH_X86 && mode != HACCSR_ARITH_FUSED_RS3) { set_error("unknown arithmetic mode %d", mode); return 1; }
   c->arith = mode;
   return 0;
 }

@@ -101,7 +101,9 @@ struct SinkRegs1 { float nx, ny, nz, ax, ay, az; };
 // 16 FMA-pipe operations and 2 other instructions (MUFU, FSETP) per pair instead of 20 + 3.  On sm_100 an FFMA2
 // occupies the issue port for two cycles, so every instruction saved shows (tools/microbench_force.cu, modes 3/5/6/7:
 // 58.7 / 70.5 / 72.7 / 75.4 % of the FP32 peak).  Oracle form FORM_FUSED restates exactly this sequence.
-template <int NC, bool GUARD0, bool COUNT, bool UNITM>
+// RS3 (HACCSR_ARITH_FUSED_RS3): (r2 + rsm^2)^-3/2 as rsqrt(s*s*s) instead of rsqrt(s)^3 -- one more FMA-pipe operation a pair,
+// a third of the rsqrt error (MUFU.RSQ's error enters once, halved by the -3/2... see DESIGN.md 3.1 for the measured distances)
+template <int NC, bool GUARD0, bool COUNT, bool UNITM, bool RS3 = false>
 __device__ __forceinline__ void interact2_fused(const float4 s, SinkRegs2 &k, const ForceParams &P, unsigned &cnt_a, unsigned &cnt_b) {
   const float2 dx = __fadd2_rn(make_float2(s.x, s.x), k.nx), dy = __fadd2_rn(make_float2(s.y, s.y), k.ny),
                dz = __fadd2_rn(make_float2(s.z, s.z), k.nz);
@@ -111,8 +113,14 @@ __device__ __forceinline__ void interact2_fused(const float4 s, SinkRegs2 &k, co
   float2 p = make_float2(P.b[NC - 1], P.b[NC - 1]);
 #pragma unroll
   for (int q = NC - 2; q >= 0; --q) p = __ffma2_rn(p, t, make_float2(P.b[q], P.b[q]));
-  const float2 rs = make_float2(rsqrt_ftz(t.x), rsqrt_ftz(t.y));
-  float2 f = __ffma2_rn(__fmul2_rn(rs, rs), rs, p);
+  float2 f;
+  if (RS3) {
+    const float2 t3 = __fmul2_rn(__fmul2_rn(t, t), t);
+    f = __fadd2_rn(make_float2(rsqrt_ftz(t3.x), rsqrt_ftz(t3.y)), p);
+  } else {
+    const float2 rs = make_float2(rsqrt_ftz(t.x), rsqrt_ftz(t.y));
+    f = __ffma2_rn(__fmul2_rn(rs, rs), rs, p);
+  }
   if (!UNITM) f = __fmul2_rn(f, make_float2(s.w, s.w));
   bool in_a = t.x < P.smax, in_b = t.y < P.smax;
   if (GUARD0) { in_a = in_a && (t.x > P.rsm2); in_b = in_b && (t.y > P.rsm2); }
@@ -120,15 +128,20 @@ __device__ __forceinline__ void interact2_fused(const float4 s, SinkRegs2 &k, co
   if (in_b) { k.ax.y = __fmaf_rn(f.y, dx.y, k.ax.y); k.ay.y = __fmaf_rn(f.y, dy.y, k.ay.y); k.az.y = __fmaf_rn(f.y, dz.y, k.az.y); }
   if (COUNT) { cnt_a += (in_a && t.x > P.rsm2) ? 1u : 0u; cnt_b += (in_b && t.y > P.rsm2) ? 1u : 0u; }
 }
-template <int NC, bool GUARD0, bool COUNT, bool UNITM>
+template <int NC, bool GUARD0, bool COUNT, bool UNITM, bool RS3 = false>
 __device__ __forceinline__ void interact1_fused(const float4 s, SinkRegs1 &k, const ForceParams &P, unsigned &cnt) {
   const float dx = __fadd_rn(s.x, k.nx), dy = __fadd_rn(s.y, k.ny), dz = __fadd_rn(s.z, k.nz);
   const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, P.rsm2)));
   float p = P.b[NC - 1];
 #pragma unroll
   for (int q = NC - 2; q >= 0; --q) p = __fmaf_rn(p, t, P.b[q]);
-  const float rs = rsqrt_ftz(t);
-  float f = __fmaf_rn(__fmul_rn(rs, rs), rs, p);
+  float f;
+  if (RS3) {
+    f = __fadd_rn(rsqrt_ftz(__fmul_rn(__fmul_rn(t, t), t)), p);
+  } else {
+    const float rs = rsqrt_ftz(t);
+    f = __fmaf_rn(__fmul_rn(rs, rs), rs, p);
+  }
   if (!UNITM) f = __fmul_rn(f, s.w);
   bool in = t < P.smax;
   if (GUARD0) in = in && (t > P.rsm2);
@@ -142,7 +155,7 @@ __device__ __forceinline__ void interact1_fused(const float4 s, SinkRegs1 &k, co
 // sources none of them is inside the cutoff.  One vote after the cutoff test then skips the polynomial, the rsqrt and
 // the accumulate for the whole warp.  Results are bit-identical to the unculled kernel: a skipped pair is exactly a
 // pair whose accumulate predicate was false.  `nfull` counts the lane-pairs that ran the force law (COUNT variant).
-template <int NC, bool GUARD0, bool COUNT, bool UNITM>
+template <int NC, bool GUARD0, bool COUNT, bool UNITM, bool RS3 = false>
 __device__ __forceinline__ void interact2_cull(const float4 s, SinkRegs2 &k, const ForceParams &P, unsigned &cnt_a, unsigned &cnt_b,
                                                unsigned &nf_a, unsigned &nf_b) {
   const float2 dx = __fadd2_rn(make_float2(s.x, s.x), k.nx), dy = __fadd2_rn(make_float2(s.y, s.y), k.ny),
@@ -156,14 +169,20 @@ __device__ __forceinline__ void interact2_cull(const float4 s, SinkRegs2 &k, con
   float2 p = make_float2(P.b[NC - 1], P.b[NC - 1]);
 #pragma unroll
   for (int q = NC - 2; q >= 0; --q) p = __ffma2_rn(p, t, make_float2(P.b[q], P.b[q]));
-  const float2 rs = make_float2(rsqrt_ftz(t.x), rsqrt_ftz(t.y));
-  float2 f = __ffma2_rn(__fmul2_rn(rs, rs), rs, p);
+  float2 f;
+  if (RS3) {
+    const float2 t3 = __fmul2_rn(__fmul2_rn(t, t), t);
+    f = __fadd2_rn(make_float2(rsqrt_ftz(t3.x), rsqrt_ftz(t3.y)), p);
+  } else {
+    const float2 rs = make_float2(rsqrt_ftz(t.x), rsqrt_ftz(t.y));
+    f = __ffma2_rn(__fmul2_rn(rs, rs), rs, p);
+  }
   if (!UNITM) f = __fmul2_rn(f, make_float2(s.w, s.w));
   if (in_a) { k.ax.x = __fmaf_rn(f.x, dx.x, k.ax.x); k.ay.x = __fmaf_rn(f.x, dy.x, k.ay.x); k.az.x = __fmaf_rn(f.x, dz.x, k.az.x); }
   if (in_b) { k.ax.y = __fmaf_rn(f.y, dx.y, k.ax.y); k.ay.y = __fmaf_rn(f.y, dy.y, k.ay.y); k.az.y = __fmaf_rn(f.y, dz.y, k.az.y); }
   if (COUNT) { cnt_a += (in_a && t.x > P.rsm2) ? 1u : 0u; cnt_b += (in_b && t.y > P.rsm2) ? 1u : 0u; nf_a++; nf_b++; }
 }
-template <int NC, bool GUARD0, bool COUNT, bool UNITM>
+template <int NC, bool GUARD0, bool COUNT, bool UNITM, bool RS3 = false>
 __device__ __forceinline__ void interact1_cull(const float4 s, SinkRegs1 &k, const ForceParams &P, unsigned &cnt, unsigned &nfull) {
   const float dx = __fadd_rn(s.x, k.nx), dy = __fadd_rn(s.y, k.ny), dz = __fadd_rn(s.z, k.nz);
   const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, P.rsm2)));
@@ -173,8 +192,13 @@ __device__ __forceinline__ void interact1_cull(const float4 s, SinkRegs1 &k, con
   float p = P.b[NC - 1];
 #pragma unroll
   for (int q = NC - 2; q >= 0; --q) p = __fmaf_rn(p, t, P.b[q]);
-  const float rs = rsqrt_ftz(t);
-  float f = __fmaf_rn(__fmul_rn(rs, rs), rs, p);
+  float f;
+  if (RS3) {
+    f = __fadd_rn(rsqrt_ftz(__fmul_rn(__fmul_rn(t, t), t)), p);
+  } else {
+    const float rs = rsqrt_ftz(t);
+    f = __fmaf_rn(__fmul_rn(rs, rs), rs, p);
+  }
   if (!UNITM) f = __fmul_rn(f, s.w);
   if (in) { k.ax = __fmaf_rn(f, dx, k.ax); k.ay = __fmaf_rn(f, dy, k.ay); k.az = __fmaf_rn(f, dz, k.az); }
   if (COUNT) { cnt += (in && t > P.rsm2) ? 1u : 0u; nfull += 1u; }
@@ -337,14 +361,14 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
       const float4 s = tile[j];
 #pragma unroll
       for (int k = 0; k < S2; ++k) {
-        if (FUSED == 2) interact2_cull<NC, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1], nf[2 * k], nf[2 * k + 1]);
-        else if (FUSED) interact2_fused<NC, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
+        if (FUSED == 2 || FUSED == 4) interact2_cull<NC, GUARD0, COUNT, UNITM, (FUSED >= 3)>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1], nf[2 * k], nf[2 * k + 1]);
+        else if (FUSED) interact2_fused<NC, GUARD0, COUNT, UNITM, (FUSED >= 3)>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
         else interact2<NC, LAW, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
       }
 #pragma unroll
       for (int k = 0; k < S1; ++k) {
-        if (FUSED == 2) interact1_cull<NC, GUARD0, COUNT, UNITM>(s, k1[k], P, cnt[2 * S2 + k], nf[2 * S2 + k]);
-        else if (FUSED) interact1_fused<NC, GUARD0, COUNT, UNITM>(s, k1[k], P, cnt[2 * S2 + k]);
+        if (FUSED == 2 || FUSED == 4) interact1_cull<NC, GUARD0, COUNT, UNITM, (FUSED >= 3)>(s, k1[k], P, cnt[2 * S2 + k], nf[2 * S2 + k]);
+        else if (FUSED) interact1_fused<NC, GUARD0, COUNT, UNITM, (FUSED >= 3)>(s, k1[k], P, cnt[2 * S2 + k]);
         else interact1<NC, LAW, GUARD0, COUNT, UNITM>(s, k1[k], P, cnt[2 * S2 + k]);
       }
     }
@@ -372,7 +396,7 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
     for (int g = 0; g < S; ++g) c64 += (g * 32 + lane < it.sink_count) ? cnt[g] : 0u;
     for (int o = 16; o > 0; o >>= 1) c64 += __shfl_down_sync(0xffffffffu, c64, o);
     if (lane == 0) atomicAdd(P.incut, c64);
-    if (FUSED == 2) {
+    if (FUSED == 2 || FUSED == 4) {
       unsigned long long f64 = 0;
 #pragma unroll
       for (int g = 0; g < S; ++g) f64 += (g * 32 + lane < it.sink_count) ? nf[g] : 0u;
@@ -460,11 +484,11 @@ __device__ __forceinline__ void run_item_rem(const WorkItem it, const ForceParam
         const float4 s = valid ? tile[j0 + lane] : make_float4(3.0e15f, 3.0e15f, 3.0e15f, 0.f);
 #pragma unroll
         for (int k = 0; k < S2; ++k) {
-          if (FUSED == 2) {
+          if (FUSED == 2 || FUSED == 4) {
             unsigned na = 0, nb = 0;
-            interact2_cull<NC, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1], na, nb);
+            interact2_cull<NC, GUARD0, COUNT, UNITM, (FUSED >= 3)>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1], na, nb);
             if (COUNT && valid) { nf[2 * k] += na; nf[2 * k + 1] += nb; }
-          } else if (FUSED) interact2_fused<NC, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
+          } else if (FUSED) interact2_fused<NC, GUARD0, COUNT, UNITM, (FUSED >= 3)>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
           else interact2<NC, LAW, GUARD0, COUNT, UNITM>(s, k2[k], P, cnt[2 * k], cnt[2 * k + 1]);
         }
       }
@@ -507,7 +531,7 @@ __device__ __forceinline__ void run_item_rem(const WorkItem it, const ForceParam
   }
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) { c64 += __shfl_down_sync(0xffffffffu, c64, o); f64 += __shfl_down_sync(0xffffffffu, f64, o); }
-    if (lane == 0) { atomicAdd(P.incut, c64); if (FUSED == 2) atomicAdd(P.incut + 1, f64); }
+    if (lane == 0) { atomicAdd(P.incut, c64); if (FUSED == 2 || FUSED == 4) atomicAdd(P.incut + 1, f64); }
   }
 }
 
@@ -759,13 +783,20 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   else if (c->law.kind == HACCSR_LAW_SR_INTERP) rc = guard0 ? launch_force<1, 3, true>(c, P, ni, count_in_cutoff) : launch_force<1, 3, false>(c, P, ni, count_in_cutoff);
   else {
     const bool guard = !(c->law.rsm2 > 0.0f);
-    if (c->arith == HACCSR_ARITH_FUSED && c->cull) {
-      if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true, 2>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false, 2>(c, P, ni, count_in_cutoff);
-      else rc = guard ? launch_force<7, 0, true, 2>(c, P, ni, count_in_cutoff) : launch_force<7, 0, false, 2>(c, P, ni, count_in_cutoff);
-    } else if (c->arith == HACCSR_ARITH_FUSED) {
-      if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true, 1>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false, 1>(c, P, ni, count_in_cutoff);
-      else rc = guard ? launch_force<7, 0, true, 1>(c, P, ni, count_in_cutoff) : launch_force<7, 0, false, 1>(c, P, ni, count_in_cutoff);
-    } else if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false>(c, P, ni, count_in_cutoff);
+    const bool fused = c->arith == HACCSR_ARITH_FUSED || c->arith == HACCSR_ARITH_FUSED_RS3;
+    // template code FUSED: 1 fused, 2 fused + culling, 3 fused with rsqrt(s^3), 4 that + culling
+    const int code = !fused ? 0 : ((c->arith == HACCSR_ARITH_FUSED_RS3 ? 3 : 1) + (c->cull ? 1 : 0));
+#define HSR_LAUNCH(CODE)                                                                                                        \
+  do {                                                                                                                          \
+    if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true, CODE>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false, CODE>(c, P, ni, count_in_cutoff); \
+    else rc = guard ? launch_force<7, 0, true, CODE>(c, P, ni, count_in_cutoff) : launch_force<7, 0, false, CODE>(c, P, ni, count_in_cutoff); \
+  } while (0)
+    if (code == 1) HSR_LAUNCH(1);
+    else if (code == 2) HSR_LAUNCH(2);
+    else if (code == 3) HSR_LAUNCH(3);
+    else if (code == 4) HSR_LAUNCH(4);
+#undef HSR_LAUNCH
+    else if (c->law.ncoef <= 6) rc = guard ? launch_force<6, 0, true>(c, P, ni, count_in_cutoff) : launch_force<6, 0, false>(c, P, ni, count_in_cutoff);
     else rc = guard ? launch_force<7, 0, true>(c, P, ni, count_in_cutoff) : launch_force<7, 0, false>(c, P, ni, count_in_cutoff);
   }
   if (rc) return rc;
@@ -773,7 +804,7 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
     HSR_CUDA(cudaMemcpyAsync(c->h_counters + 11, c->d_counters + 11, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     HSR_CUDA(cudaStreamSynchronize(s));
     st->pairs_in_cutoff = (uint64_t)c->h_counters[11];
-    st->pairs_force_law = (c->arith == HACCSR_ARITH_FUSED && c->cull && c->law.kind == HACCSR_LAW_SR_POLY)
+    st->pairs_force_law = ((c->arith == HACCSR_ARITH_FUSED || c->arith == HACCSR_ARITH_FUSED_RS3) && c->cull && c->law.kind == HACCSR_LAW_SR_POLY)
                               ? (uint64_t)c->h_counters[12] : st->pairs_evaluated;
   }
   return 0;

@@ -504,7 +504,7 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 // and leaves the warps waiting at the barrier behind the look-back (measured: 54 % of all stall samples, 0.7 ms per
 // level); with the count one iteration ahead a block can run an iteration ahead of its neighbours.
 template <int PTPB>
-__global__ void __launch_bounds__(PTPB, 512 / PTPB) k_split_pass(const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
+__global__ void __launch_bounds__(PTPB + 32, PTPB == 256 ? 2 : 3) k_split_pass(const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
                                                        const int *__restrict__ nid, Node *__restrict__ nodes,
                                                        NodeAcc *__restrict__ acc, const float *__restrict__ scales,
                                                        BuildState *__restrict__ st, unsigned long long *__restrict__ desc,
@@ -607,18 +607,20 @@ __global__ void __launch_bounds__(PTPB, 512 / PTPB) k_split_pass(const float4 *_
     }
   };
   const int nk = T00 < ntiles ? (ntiles - T00 + G - 1) / G : 0;     // tiles of this block
-  if (t == 0) for (int k = 0; k < NST - 1; ++k) issue(k);
-  if (nk > 0) stage_a(0);
+  // The block is PTPB worker threads plus one helper warp.  The helper posts the bulk copies, sums the look-back words of
+  // the tile the workers are about to finish while they run the A stage of the next one (the look-back is one or two L2
+  // round trips: with warp 0 doing it between the barriers the other warps stood waiting, 30 % of all stall samples), and
+  // scans / publishes the A stage's entries behind the barrier.
+  const bool helper = t >= PTPB;
+  if (helper && lane == 0) for (int k = 0; k < NST - 1; ++k) issue(k);
+  if (!helper && nk > 0) stage_a(0);
   __syncthreads();
-  if (w == 0 && nk > 0) scan_publish(0);
+  if (helper && nk > 0) scan_publish(0);
   __syncthreads();
   for (int k = 0; k < nk; ++k) {
     const int T0 = T00 + k * G, q = k % NST, tile0 = T0 * PT;
-    if (t == 0) issue(k + NST - 1);           // its slot was tile k-1's: every thread left it before the last barrier
-    if (k + 1 < nk) stage_a(k + 1);
-    __syncthreads();
-    if (w == 0) {
-      if (k + 1 < nk) scan_publish(k + 1);
+    if (helper) {
+      if (lane == 0) issue(k + NST - 1);      // its slot was tile k-1's: every thread left it before the last barrier
       unsigned carry = 0;
       if (s_misc[q][0]) {
         carry = lookback<LB_W>(desc, T0 - 1, epoch, lane);
@@ -626,10 +628,16 @@ __global__ void __launch_bounds__(PTPB, 512 / PTPB) k_split_pass(const float4 *_
         if (own >= 0 && lane == 0) desc_store(desc + T0, desc_make(epoch, ST_PREFIX, carry + (unsigned)own));
       }
       if (lane == 0) s_misc[q][2] = (int)carry;
+    } else if (k + 1 < nk) {
+      stage_a(k + 1);
     }
     __syncthreads();
+    if (helper && k + 1 < nk) scan_publish(k + 1);
+    __syncthreads();
+    const int cbase = s_misc[q][1];          // in a register: the helper recycles the slot's words while the slots are flushed
+    if (!helper) {
     // ---- B stage: destinations and stores ----------------------------------------------------------------------------------
-    const int carry = s_misc[q][2], cbase = s_misc[q][1];
+    const int carry = s_misc[q][2];
     const unsigned char *sl = ring + (size_t)q * SLOT_BYTES;
     const int *nidS = reinterpret_cast<const int *>(sl + SLOT_NID);
     const float4 *recS = reinterpret_cast<const float4 *>(sl + SLOT_REC);
@@ -639,46 +647,38 @@ __global__ void __launch_bounds__(PTPB, 512 / PTPB) k_split_pass(const float4 *_
     unsigned fl = 0;         // bit j: left flag of item j
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
+      // one straight-line body for the three kinds of particle (finished earlier / leaf now / moving to a child): the
+      // stores go through selected pointers instead of three branches
       const int p = j * PTPB + t, i = tile0 + p;
-      cl[j] = 0;
-      if (i >= n) continue;
-      const int ndv = nidS[p];
-      if (ndv < 0) { nid_out[i] = -1; continue; }
-      const float4 *np = reinterpret_cast<const float4 *>(nodes + ndv);
+      const int ndv = i < n ? nidS[p] : -1;
+      const bool act = ndv >= 0;
+      const float4 *np = reinterpret_cast<const float4 *>(nodes + (act ? ndv : 0));
       const float4 a = __ldg(np), d = __ldg(np + 3);
       int cnt = __float_as_int(a.x), off = __float_as_int(a.y);
-      cl[j] = __float_as_int(a.z);
+      cl[j] = act ? __float_as_int(a.z) : 0;
       r[j] = recS[p];
       const unsigned ix = idxS[p];
-      if (cl[j] <= 0) {                      // the node is a leaf (or an orphan holding a degenerate node's particles): final place
-        int fin = i;
-        if (__float_as_int(d.w) == -2) {     // reversed: mirror the leaf (an orphan has its parent's range)
-          if (cnt == 0) {
-            const float4 pa = __ldg(reinterpret_cast<const float4 *>(nodes + __float_as_int(d.z)));
-            cnt = __float_as_int(pa.x); off = __float_as_int(pa.y);
-          }
-          fin = 2 * off + cnt - 1 - i;
-        }
-        src4[fin] = r[j]; perm[fin] = ix; nid_out[i] = -1;
-        continue;
+      const bool split = cl[j] > 0;
+      if (act && !split && __float_as_int(d.w) == -2 && cnt == 0) {     // reversed orphan (rare): its parent's range
+        const float4 pa = __ldg(reinterpret_cast<const float4 *>(nodes + __float_as_int(d.z)));
+        cnt = __float_as_int(pa.x); off = __float_as_int(pa.y);
       }
+      // a leaf (or an orphan holding a degenerate node's particles) reaches its final place; a reversed one is mirrored
+      const int fin = (__float_as_int(d.w) == -2) ? 2 * off + cnt - 1 - i : i;
       const int e = j * (PTPB / 32) + w;
       const unsigned fb = s_fb[q][e], hb = s_hb[q][e];
       const unsigned hm = hb & (below | (1u << lane));      // node starts at or before this lane in its row
-      int lb;
-      if (hm) {
-        lb = __popc(fb & below & ~((1u << (31 - __clz(hm))) - 1u));
-      } else {
-        lb = s_cv[q][e] + __popc(fb & below);
-        if (!s_cf[q][e]) lb += carry;                         // the node started in an earlier tile
-      }
+      const int hl = 31 - __clz(hm | 1u);                      // last such start (0 if none: masked below)
+      int lb = __popc(fb & below & ~((1u << hl) - 1u));
+      if (!hm) lb = s_cv[q][e] + __popc(fb & below) + (s_cf[q][e] ? 0 : carry);     // the node started in an earlier row / tile
       const int flag = (fb >> lane) & 1u;
       fl |= (unsigned)flag << j;
-      int dest, child;
-      if (flag) { dest = off + lb; child = cl[j]; }
-      else { dest = off + cnt - 1 - ((i - off) - lb); child = cl[j] + 1; }
-      rec_out[dest] = r[j]; idx_out[dest] = ix; nid_out[dest] = child;
-      if (i == off + cnt - 1) {                               // the node's last particle knows the split
+      const int dest = flag ? off + lb : off + cnt - 1 - ((i - off) - lb);
+      float4 *prec = split ? rec_out + dest : src4 + fin;
+      unsigned *pidx = split ? idx_out + dest : perm + fin;
+      if (act) { *prec = r[j]; *pidx = ix; }
+      if (i < n) nid_out[split ? dest : i] = split ? cl[j] + 1 - flag : -1;
+      if (split && i == off + cnt - 1) {                      // the node's last particle knows the split
         const int is = lb + flag;
         nodes[cl[j]].count = is;            nodes[cl[j]].offset = off;              // :731-746
         nodes[cl[j] + 1].count = cnt - is;  nodes[cl[j] + 1].offset = off + is;     // :732,762
@@ -753,6 +753,7 @@ __global__ void __launch_bounds__(PTPB, 512 / PTPB) k_split_pass(const float4 *_
         key = __reduce_min_sync(0xffffffffu, next);
       }
     }
+    }   // workers
     __syncthreads();
     if (t < NSLOT && slots[t].used) {
       NodeAcc &A = acc[cbase + t];
@@ -1030,7 +1031,7 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
     const void *fn = want == 256 ? (const void *)k_split_pass<256> : (const void *)k_split_pass<128>;
     const size_t dyn = (size_t)NST * want * IPT * 24;
     HSR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sp, fn, want, dyn));
+    HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sp, fn, want + 32, dyn));
     if (occ_sp < 1) { occ_sp = 0; set_error("k_split_pass does not fit on an SM"); return 2; }
     ptpb = want;
   }
@@ -1110,7 +1111,7 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
           float4 *a14 = c->src4.p; unsigned *a15 = c->perm.p;
           void *args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11, &a12, &a13, &a14, &a15};
           const void *fn = ptpb == 256 ? (const void *)k_split_pass<256> : (const void *)k_split_pass<128>;
-          HSR_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid_sp), dim3(ptpb), args, (size_t)NST * PT * 24, st));
+          HSR_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid_sp), dim3(ptpb + 32), args, (size_t)NST * PT * 24, st));
         }
         c->launches += 2;
         float4 *tr = rec; rec = rec_o; rec_o = tr;

@@ -57,8 +57,12 @@ enum {
  *          Accelerations agree with the x86-64 reference build within FP32 rounding (tests: 1e-5 of the gross sum);
  *          pairs within one ulp of the cutoff may fall on the other side (their force is ~1e-5 of a typical pair's).
  *   X86:   r2 = (dx*dx + dy*dy) + dz*dz unfused, in the order of the x86-64 build of the reference: the set of
- *          pairs inside the cutoff is bit-identical to that build's. */
-enum { HACCSR_ARITH_FUSED = 0, HACCSR_ARITH_X86 = 1 };
+ *          pairs inside the cutoff is bit-identical to that build's.
+ *   FUSED_RS3: FUSED with (r2 + rsm^2)^-3/2 formed as rsqrt(s*s*s) (the x86 order of that step) instead of rsqrt(s)^3: one more
+ *          FMA-pipe operation a pair (17 instead of 16), and the MUFU.RSQ error enters once instead of three times, so the
+ *          distance to the FP64 sum of the same pairs comes down to the CPU reference's own (profiles/parity_r2.json).
+ *          Same set of in-cutoff pairs as FUSED. */
+enum { HACCSR_ARITH_FUSED = 0, HACCSR_ARITH_X86 = 1, HACCSR_ARITH_FUSED_RS3 = 2 };
 
 /* Mirrors RCBForceTree::printStats (RCBForceTree.cxx:460-511) plus the measurement fields of
  * SURVEY.md section 8(d). */

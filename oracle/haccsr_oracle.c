@@ -662,7 +662,7 @@ void orc_direct_sum(int64_t n, const float *x, const float *y, const float *z, c
  * PINNED: bit-for-bit equal to the reference's own loops.  Particles.cxx as a whole needs MPI, Domain and the initializer
  * headers, but the three functions involved do not: oracle/build_ref.sh cuts them out of the file where it lies and compiles
  * them between a small scaffold (oracle/stubs/cic_pre.h, cic_post.cxx) into oracle/_ref/libhaccref_cic.so; the fixture
- * tests/golden/ref_cic_clustered12k.npz holds that library's outputs (tests/golden/make_golden_cic.py) and
+ * tests/golden/cic_ref_clustered12k.npz holds that library's outputs (tests/golden/make_golden_cic.py) and
  * tests/test_cic_cpu.py asserts equality with the fixture and, where the library is present, live.  Restated line by line
  * under C's promotion rules (`1.0` literals are double). */
 static int64_t orc_array_index(int xx, int yy, int zz, const int *ng, int64_t safe) {          /* :373-395 */

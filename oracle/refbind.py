@@ -103,11 +103,30 @@ def rcb_kick(p, tree_lo, tree_hi, force_lo, force_hi, rsm, theta, ppn, fcoeff=1.
     coef = np.ascontiguousarray(coef, dtype=np.float32)
     st = RefStats()
     lib.ref_set_tdpts(int(tdpts))       # 1: RCBMonopoleForceTree, 12: RCBQuadrupoleForceTree
-    rc = lib.ref_rcb_kick(law, _fp(coef), len(coef), int(count_pairs), int(quiet), n,
-                          _fp(q["x"]), _fp(q["y"]), _fp(q["z"]), _fp(q["vx"]), _fp(q["vy"]), _fp(q["vz"]),
-                          _fp(q["mass"]), _fp(q["phi"]), q["id"].ctypes.data_as(C.POINTER(C.c_int64)),
-                          q["mask"].ctypes.data_as(C.POINTER(C.c_uint16)), _fp(boxes), rsm, theta,
-                          ppn, ds, tmin, fcoeff, int(keep_tree), C.byref(st))
+
+    def call():
+        return lib.ref_rcb_kick(law, _fp(coef), len(coef), int(count_pairs), int(quiet), n,
+                                _fp(q["x"]), _fp(q["y"]), _fp(q["z"]), _fp(q["vx"]), _fp(q["vy"]), _fp(q["vz"]),
+                                _fp(q["mass"]), _fp(q["phi"]), q["id"].ctypes.data_as(C.POINTER(C.c_int64)),
+                                q["mask"].ctypes.data_as(C.POINTER(C.c_uint16)), _fp(boxes), rsm, theta,
+                                ppn, ds, tmin, fcoeff, int(keep_tree), C.byref(st))
+    if vmax:
+        # the reference keeps 4 * VMAX floats of list on the stack of whichever thread walks a leaf (RCBForceTree.cxx:940),
+        # 16 MB with VMAX raised to 2^20: the OpenMP workers get theirs from OMP_STACKSIZE, but the calling thread is the
+        # OpenMP master and the process's main stack is 8 MB (a segmentation fault in the middle of the walk, round 1's
+        # "--state clumpy" crash).  The call therefore runs on a thread with a stack of its own.
+        import threading
+        box = {}
+        old = threading.stack_size(512 << 20)
+        try:
+            th = threading.Thread(target=lambda: box.setdefault("rc", call()))
+            th.start()
+        finally:
+            threading.stack_size(old)
+        th.join()
+        rc = box.get("rc", -1)
+    else:
+        rc = call()
     assert rc == 0, rc
     stats = {f: getattr(st, f) for f, _ in RefStats._fields_}
     tree = None

@@ -29,7 +29,7 @@ rho = R.cic(p, ng, gpscal)
 grid = rng.standard_normal(ng).astype(np.float32)
 tau, fscal = np.float32(0.37), np.float32(1.9)
 out = {("out_" + k): R.inverse_cic(p, grid, tau, fscal, comp) for comp, k in enumerate(("vx", "vy", "vz", "phi"))}
-path = os.path.join(HERE, "ref_cic_clustered12k.npz")
+path = os.path.join(HERE, "cic_ref_clustered12k.npz")
 np.savez_compressed(path, x=p["x"], y=p["y"], z=p["z"], vx=p["vx"], vy=p["vy"], vz=p["vz"], phi=p["phi"], ng=np.asarray(ng, np.int32),
                     gpscal=gpscal, c=c, rho=rho, grid=grid, tau=tau, fscal=fscal, **out)
 print(path, os.path.getsize(path), float(rho.sum()), float(rho.max()))

@@ -1,7 +1,7 @@
 """CPU tests of the CIC restatement (oracle/haccsr_oracle.c: orc_cic, orc_inverse_cic; reference src/cpu/Particles.cxx:589-714).
 PINNED: bit-for-bit equal to the reference's own loops -- Particles::array_index / cic / inverse_cic cut out of Particles.cxx and
 compiled by oracle/build_ref.sh into oracle/_ref/libhaccref_cic.so (the file as a whole needs MPI, the three functions do not) --
-through the committed fixture tests/golden/ref_cic_clustered12k.npz (tests/golden/make_golden_cic.py) and, where the compiled
+through the committed fixture tests/golden/cic_ref_clustered12k.npz (tests/golden/make_golden_cic.py) and, where the compiled
 reference is present, live.  Plus properties any correct cloud-in-cell pair has and an independent float64 evaluation."""
 import numpy as np
 import pytest
@@ -100,7 +100,7 @@ def test_inverse_cic_matches_float64_and_is_adjoint_of_cic(oracle, snap):
     assert abs(lhs - rhs) <= 1e-4 * abs(rhs) + 1e-3
 
 
-GOLD = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "ref_cic_clustered12k.npz")
+GOLD = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "cic_ref_clustered12k.npz")
 
 
 def load_cic_golden():

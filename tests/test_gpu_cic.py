@@ -1,6 +1,6 @@
 """GPU tests (-m gpu) of the PM coupling kernels (csrc/cic.cu) through the C ABI against the reference's own loops
 (Particles::cic / Particles::inverse_cic, reference src/cpu/Particles.cxx:589-714): the committed fixture generated from the
-compiled reference (tests/golden/ref_cic_clustered12k.npz) and the oracle restatement that is bit-equal to it."""
+compiled reference (tests/golden/cic_ref_clustered12k.npz) and the oracle restatement that is bit-equal to it."""
 import numpy as np
 import pytest
 

@@ -20,7 +20,7 @@ import pytest
 
 import hacc_coral_b200 as H
 from hacc_coral_b200 import synth
-from tests.util import RSM, THETA, accel_errors, boxes, by_id, compare_trees
+from tests.util import EDGE, RSM, THETA, accel_errors, boxes, by_id, compare_trees
 
 pytestmark = pytest.mark.gpu
 
@@ -700,3 +700,30 @@ def test_culling_changes_no_bit(tdpts):
     assert sts[0]["pairs_evaluated"] == sts[1]["pairs_evaluated"] and sts[0]["pairs_in_cutoff"] == sts[1]["pairs_in_cutoff"]
     assert sts[0]["pairs_force_law"] == sts[0]["pairs_evaluated"]
     assert sts[1]["pairs_in_cutoff"] <= sts[1]["pairs_force_law"] < 0.8 * sts[1]["pairs_evaluated"]
+
+
+@pytest.mark.parametrize("ppn", [64, 128, 256])
+def test_tuned_leaf_size_against_reference_at_512(oracle, ppn):
+    """Time to solution: a smaller leaf size evaluates fewer list pairs for the same physical interactions (SURVEY.md 8(c):
+    2.0 k instead of 7.6 k pairs per particle at -N 128).  The kicked SET near the faces depends on leaf geometry
+    (RCBForceTree.cxx:1166-1172), so the cross-ppn gate is on the particles strictly inside the force box: against the
+    reference at its shipped -N 512, the in-cutoff pair set of each such particle is the same (no node is accepted as a
+    monopole at this density: leaf boxes >> 0.546 rmax), so its kick differs by FP32 summation order only."""
+    n = 40
+    p = synth.zeldovich(n, z=50.0, seed=9, ghost=0)
+    b = boxes(n)
+    o = oracle.run(p, *b, RSM, THETA, 512, form=oracle.FORM_GENERIC)             # bit-equal to the compiled reference
+    og = oracle.run(p, *b, RSM, THETA, 512, form=oracle.FORM_GROSS)
+    out, st, _, _ = gpu_run(p, b, THETA, ppn, want_tree=False, arith=H.ARITH_X86)
+    assert st["pseudo_particles"] == 0
+    assert st["pairs_evaluated"] < o["stats"]["pairs_eval"]                        # fewer list pairs ...
+    a, r = by_id(out, ("vx", "vy", "vz", "x", "y", "z")), by_id(o, ("vx", "vy", "vz"))
+    gross = np.maximum(by_id(og)["vx"].astype(np.float64), 1e-30)
+    inside = np.ones(a["x"].size, bool)
+    for k in ("x", "y", "z"):
+        inside &= (a[k] > EDGE) & (a[k] < n - EDGE)
+    assert inside.sum() > 0.5 * inside.size
+    d = _dist(a, r)
+    assert (d[inside] / gross[inside]).max() <= 1e-5                               # ... the same kicks
+    rel, _, _, _ = accel_errors({k: a[k][inside] for k in ("vx", "vy", "vz")}, {k: r[k][inside] for k in ("vx", "vy", "vz")})
+    assert np.median(rel) <= 5e-6 and np.quantile(rel, 0.99) <= 1e-4
