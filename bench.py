@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--sample-side", type=int, default=0,
                     help="cut-out side (cells) for the CPU baseline; 0 = sized from a calibration run so the arm stays within --cpu-budget")
     ap.add_argument("--cpu-budget", type=float, default=100.0, help="seconds of CPU reference work allowed in total (reference arm)")
-    ap.add_argument("--arith", default="fused", choices=["fused", "x86"], help="pair-kernel arithmetic (include/haccsr.h)")
+    ap.add_argument("--arith", default="fused", choices=["fused", "x86", "fused_rs3"], help="pair-kernel arithmetic (include/haccsr.h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--subcycle", type=int, default=5, metavar="NSUB",
                     help="sub-cycles per long step for the Level-2 end-to-end path (haccsr_subcycle; reference indat nsub = 5); 0 = skip")
@@ -271,7 +271,7 @@ class Bench:
         with NumaLocal(self.local):
             self.pin = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in self.p.items()}
             self.work = {k: torch.from_numpy(v.copy()).pin_memory().numpy() for k, v in self.p.items()}
-        g = H.HaccSR(self.n, device=self.local, arith=H.ARITH_FUSED if args.arith == "fused" else H.ARITH_X86)
+        g = H.HaccSR(self.n, device=self.local, arith={"fused": H.ARITH_FUSED, "x86": H.ARITH_X86, "fused_rs3": H.ARITH_FUSED_RS3}[args.arith])
         g.set_force_law(H.LAW_SR_POLY, H.POLY5, RSM, H.RMAX)
         g.set_culling(args.cull)
         g.set_stream(self.stream.cuda_stream)
@@ -349,6 +349,85 @@ class Bench:
         self.g.upload(self.pin)
         return out
 
+    def e2e_long_step(self, nsub, reps):
+        """Level-3 path: the particles never leave the GPU.  One long step = the particle side of the PM solve on the device
+        (haccsr_cic: deposit, density grid to the host; haccsr_inverse_cic x 3: the three gradient grids from the host,
+        Particles.cxx:589-714, mc3.cxx:304-379) around the short-range sub-cycle (haccsr_subcycle, nsub kicks).  Only the PM
+        grids cross PCIe: nglt^3 floats down, 3 nglt^3 floats up per long step.  The FFT Poisson solve between deposit and
+        gradient stays the reference's (src/dfft) and is not part of the timed region: the gradient grids are synthetic."""
+        torch = self.torch
+        ng = (self.nglt,) * 3
+        ncell = self.nglt ** 3
+        with NumaLocal(self.local):
+            rho = torch.empty(ng, dtype=torch.float32).pin_memory().numpy()
+            grads = [(torch.randn(ng, dtype=torch.float32) * 1e-4).pin_memory().numpy() for _ in range(3)]
+        vmax = max(float(np.abs(self.pin[k]).max()) for k in ("vx", "vy", "vz"))
+        pt = 0.02 / vmax if vmax > 0 else 0.01
+        sub_args = (nsub, pt, [float(self.nglt)] * 3, self.lo, self.hi, self.flo, self.fhi, THETA, self.args.ppn, 1e-3)
+
+        def step():
+            self.g.cic(ng, 1.0, out=rho)
+            for comp in range(3):
+                self.g.inverse_cic(grads[comp], 1e-3, 1.0, comp)
+            return self.g.subcycle(*sub_args)
+        self.g.upload(self.pin)
+        step()                                             # warm
+        self.barrier()
+        e = self.events(2)
+        e[0].record(self.stream)
+        pairs, ms_cic = 0, 0.0
+        for _ in range(reps):
+            c = self.events(3)
+            c[0].record(self.stream)
+            self.g.cic(ng, 1.0, out=rho)
+            c[1].record(self.stream)
+            for comp in range(3):
+                self.g.inverse_cic(grads[comp], 1e-3, 1.0, comp)
+            c[2].record(self.stream)
+            pairs += self.g.subcycle(*sub_args)["pairs_evaluated"]
+            self.torch.cuda.synchronize()
+            ms_cic += c[0].elapsed_time(c[2])
+        e[1].record(self.stream)
+        self.barrier()
+        out = {"pairs": pairs, "ms": e[0].elapsed_time(e[1]), "ms_pm_coupling": ms_cic / reps, "reps": reps, "nsub": nsub,
+               "h2d": 3 * 4 * ncell, "d2h": 4 * ncell}
+        self.g.upload(self.pin)
+        return out
+
+    def cic_block(self):
+        """Device time of the deposit and of one interpolation with the grids already on the device (HBM-bound kernels)."""
+        torch = self.torch
+        import ctypes as C
+        ng = (self.nglt,) * 3
+        ncell = self.nglt ** 3
+        grid = torch.randn(ng, dtype=torch.float32, device=self.dev)
+        rho = torch.empty(ng, dtype=torch.float32, device=self.dev)
+        ng3 = (C.c_int32 * 3)(*ng)
+        lib, h = self.g.lib, self.g._h
+        lib.haccsr_cic(h, ng3, 1.0, C.c_void_p(rho.data_ptr()), 1)
+        lib.haccsr_inverse_cic(h, ng3, C.c_void_p(grid.data_ptr()), 1, 0.0, 1.0, 3)
+        e = self.events(3)
+        self.torch.cuda.synchronize()
+        e[0].record(self.stream)
+        for _ in range(3):
+            lib.haccsr_cic(h, ng3, 1.0, C.c_void_p(rho.data_ptr()), 1)
+        e[1].record(self.stream)
+        for _ in range(3):
+            lib.haccsr_inverse_cic(h, ng3, C.c_void_p(grid.data_ptr()), 1, 0.0, 1.0, 3)      # tau = 0: phi unchanged
+        e[2].record(self.stream)
+        self.torch.cuda.synchronize()
+        t_cic, t_inv = e[0].elapsed_time(e[1]) / 3, e[1].elapsed_time(e[2]) / 3
+        pk, _ = peaks()
+        hbm = float(pk.get("hbm_gbs", 6650.0))
+        # algorithmic bytes: deposit = 12 B of position per particle + 8 B accumulator zero + 8 B read + 4 B write per cell;
+        # interpolation = 12 B position + 4 B read + 4 B write of the updated array per particle + 4 B per cell
+        b_cic, b_inv = 12.0 * self.n + 20.0 * ncell, 20.0 * self.n + 4.0 * ncell
+        return {"ms_cic": t_cic, "ms_inverse_cic": t_inv, "cic_GBps": b_cic / (t_cic * 1e-3) / 1e9, "inverse_cic_GBps": b_inv / (t_inv * 1e-3) / 1e9,
+                "cic_frac_of_hbm": b_cic / (t_cic * 1e-3) / 1e9 / hbm, "inverse_cic_frac_of_hbm": b_inv / (t_inv * 1e-3) / 1e9 / hbm,
+                "atomics_per_particle": 8, "grid": list(ng),
+                "note": "haccsr_cic / haccsr_inverse_cic with device grids (Particles::cic / inverse_cic, Particles.cxx:589-714); the "
+                        "deposit is bound by its 8 scattered 64-bit atomics per particle (L2), not by HBM"}
+
     def pcie(self):
         """Host<->device copy rates of the ten arrays with every rank copying at the same time."""
         self.barrier()
@@ -408,10 +487,12 @@ def block_for_state(B, args, steps, warmup, world, sampler=None):
     e2e = B.e2e_facade(max(1, min(steps, 3)))
     B.g.upload(B.pin)
     sub = B.e2e_subcycle(args.subcycle, 2 if steps > 2 else 1) if args.subcycle > 0 else None
+    lng = B.e2e_long_step(args.subcycle, 2 if steps > 2 else 1) if args.subcycle > 0 else None
     h2d, d2h = B.pcie()
     stc = B.kick(count_in_cutoff=True)     # one untimed pass that also counts the pairs inside the cutoff
-    tv = [acc["ms"], e2e["ms"], sub["ms"] if sub else 0.0, -h2d, -d2h]
-    sv = [float(acc["pairs"]), float(e2e["pairs"]), float(sub["pairs"]) if sub else 0.0, float(acc["launches"])]
+    tv = [acc["ms"], e2e["ms"], sub["ms"] if sub else 0.0, -h2d, -d2h, lng["ms"] if lng else 0.0]
+    sv = [float(acc["pairs"]), float(e2e["pairs"]), float(sub["pairs"]) if sub else 0.0, float(acc["launches"]),
+          float(lng["pairs"]) if lng else 0.0]
     tvt = torch.tensor(tv, device=B.dev, dtype=torch.float64)
     svt = torch.tensor(sv, device=B.dev, dtype=torch.float64)
     if B.dist is not None:
@@ -454,6 +535,14 @@ def block_for_state(B, args, steps, warmup, world, sampler=None):
             "h2d_bytes_per_kick": 42 * n // sub["nsub"], "d2h_bytes_per_kick": 42 * n // sub["nsub"],
             "ms_per_kick_resident_this_rank": sub["ms_resident"] / kicks,
             "path": "haccsr_upload + haccsr_subcycle(nsub) + haccsr_download (INTEGRATION.md Level 2 = Particles::subCycle, Particles.cxx:1176-1201)"}
+    if lng:
+        kicks = lng["reps"] * lng["nsub"]
+        out["e2e"]["long_step"] = {
+            "value": sv[4] / (tv[5] * 1e-3) / 1e9, "unit": "Ginteractions/s", "nsub": lng["nsub"], "ms_per_kick": tv[5] / kicks,
+            "h2d_bytes_per_step": lng["h2d"], "d2h_bytes_per_step": lng["d2h"], "ms_pm_coupling_this_rank": lng["ms_pm_coupling"],
+            "path": "particles resident across the long step (INTEGRATION.md Level 3): haccsr_cic (density grid to the host) + "
+                    "3 x haccsr_inverse_cic (gradient grids from the host) + haccsr_subcycle(nsub); only the PM grids cross PCIe; "
+                    "the reference's FFT solve between deposit and gradient is outside the timed region (synthetic gradient grids)"}
     return out, acc, stc
 
 
@@ -498,7 +587,8 @@ def main():
     B.load(args.state)
     sampler = ClockSampler(local)
     head, acc, stc = block_for_state(B, args, args.steps, args.warmup, world, sampler)
-    culled = B.culled(acc["ms_force"] / args.steps) if args.arith == "fused" else None
+    culled = B.culled(acc["ms_force"] / args.steps) if args.arith != "x86" else None
+    cic = B.cic_block()
     tuned = None
     if args.tune_ppn:
         rows = B.tuned([int(t) for t in args.tune_ppn.split(",")], stc["pairs_in_cutoff"])
@@ -526,7 +616,7 @@ def main():
         clustered, acc_c, _ = block_for_state(B, args, steps_c, 3, world)
         clustered["config"] = config_for("clustered")
         clustered["steps"] = steps_c
-        if args.arith == "fused":
+        if args.arith != "x86":
             clustered["culled"] = B.culled(acc_c["ms_force"] / steps_c)
     B.g.close()
     B.g = None
@@ -556,6 +646,7 @@ def main():
         line["culled"] = culled
     if tuned:
         line["tuned"] = tuned
+    line["cic"] = cic
     if clustered:
         line["clustered"] = clustered
     if refresh:

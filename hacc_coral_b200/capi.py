@@ -260,10 +260,12 @@ class HaccSR:
         return st.as_dict()
 
     # ---- PM coupling (csrc/cic.cu) ----
-    def cic(self, ng, c):
-        """Particles::cic on the resident particles; returns the (ng0, ng1, ng2) float32 density grid."""
+    def cic(self, ng, c, out=None):
+        """Particles::cic on the resident particles; returns the (ng0, ng1, ng2) float32 density grid (written into `out`,
+        e.g. a page-locked array, when given)."""
         ng3 = (C.c_int32 * 3)(*[int(t) for t in ng])
-        rho = np.empty(tuple(int(t) for t in ng), dtype=np.float32)
+        rho = out if out is not None else np.empty(tuple(int(t) for t in ng), dtype=np.float32)
+        assert rho.dtype == np.float32 and rho.flags["C_CONTIGUOUS"] and rho.size == int(np.prod([int(t) for t in ng]))
         self._check(self.lib.haccsr_cic(self._h, ng3, float(c), C.c_void_p(rho.ctypes.data), 0))
         return rho
 
