@@ -461,7 +461,24 @@ __global__ void __launch_bounds__(NTPB) k_level_nodes(Node *__restrict__ nodes, 
 // predecessors' words back to the nearest prefix (decoupled look-back, one L2 round trip for 32*LB_W tiles).  Inside the
 // tile a segmented scan over the 32 per-(row, warp) ballots gives every particle the lefts since the last node start.
 static constexpr int NSLOT = 32;       // children of one tile accumulated in shared memory (more: straight to global)
-static constexpr int LB_W = 8;         // look-back windows read at once
+// Per-child accumulators of one tile in shared memory.  The four centroid sums are kept as three 21-bit limbs each in 32-bit
+// words (native ATOMS.ADD; a 64-bit shared atomicAdd compiles to a compare-and-swap loop): a warp contributes less than 2^26 per
+// limb, a tile's eight warps less than 2^29.
+struct PassSlot {
+  unsigned umin[3], umax[3];
+  unsigned used, pad;
+  int limb[4][3];
+};
+__device__ __forceinline__ void pslot_reset(PassSlot &S) {
+  S.umin[0] = S.umin[1] = S.umin[2] = 0xffffffffu; S.umax[0] = S.umax[1] = S.umax[2] = 0u;
+  S.used = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { S.limb[q][0] = 0; S.limb[q][1] = 0; S.limb[q][2] = 0; }
+}
+#ifndef HSR_LBW
+#define HSR_LBW 1
+#endif
+static constexpr int LB_W = HSR_LBW;   // look-back windows read at once
 static constexpr int NST = 4;          // tiles of the shared-memory ring: B stage, A stage, two in flight
 
 __device__ __forceinline__ unsigned tb_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -521,7 +538,7 @@ __global__ void __launch_bounds__(PTPB + 32, PTPB == 256 ? 2 : 3) k_split_pass(c
   __shared__ int s_ev[32], s_ef[32];                  // A stage: lefts behind the entry's last node start (or all of them), has a node start
   __shared__ int s_misc[NST][4];   // per slot: [0] first node started in an earlier tile, [1] smallest child id, [2] carry, [3] own word
   __shared__ unsigned long long s_bar[NST];
-  __shared__ Slot slots[NSLOT];
+  __shared__ PassSlot slots[NSLOT];
   if (st->error || (level > 0 && st->nsplit[level - 1] <= 0)) return;     // the tree was finished by an earlier pass
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const unsigned epoch = (unsigned)level + 1u;
@@ -533,7 +550,7 @@ __global__ void __launch_bounds__(PTPB + 32, PTPB == 256 ? 2 : 3) k_split_pass(c
     for (int q = 0; q < NST; ++q) { tb_mbar_init(tb_smem_u32(&s_bar[q]), 1); s_misc[q][0] = 0; s_misc[q][1] = INT_MAX; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (t < NSLOT) slot_reset(slots[t]);
+  if (t < NSLOT) pslot_reset(slots[t]);
   if (t < 32) { s_ev[t] = 0; s_ef[t] = 0; }           // entries beyond NE stay neutral in the scan
   __syncthreads();
   // one thread posts the three bulk copies of tile number k of this block
@@ -562,21 +579,18 @@ __global__ void __launch_bounds__(PTPB + 32, PTPB == 256 ? 2 : 3) k_split_pass(c
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
       const int p = j * PTPB + t, i = tile0 + p;
-      int flag = 0, head = 0;
       const int ndv = i < n ? nidS[p] : -1;
-      if (ndv >= 0) {
-        const float4 *np = reinterpret_cast<const float4 *>(nodes + ndv);
-        const float4 a = __ldg(np), c = __ldg(np + 2), d = __ldg(np + 3);     // independent loads: one L2 round trip
-        const int cl = __float_as_int(a.z);
-        if (cl > 0) {                                                            // the node splits at this level
-          const int sp = __float_as_int(d.w) & 3, off = __float_as_int(a.y);
-          const float pivot = sp == 0 ? c.z : (sp == 1 ? c.w : d.x);             // xc[sp], RCBForceTree.cxx:720
-          flag = recS[4 * p + sp] < pivot;                                       // :640
-          head = i == off;
-          cmin = min(cmin, cl);
-          if (p == 0 && off < tile0) s_misc[q][0] = 1;
-        }
-      }
+      // unconditional loads (node 0 for a finished particle): the twelve node loads of a thread's four items go out together
+      const float4 *np = reinterpret_cast<const float4 *>(nodes + max(ndv, 0));
+      const float4 a = __ldg(np), c = __ldg(np + 2), d = __ldg(np + 3);
+      const int cl = ndv >= 0 ? __float_as_int(a.z) : 0;
+      const bool split = cl > 0;                                                 // the node splits at this level
+      const int sp = __float_as_int(d.w) & 3, off = __float_as_int(a.y);
+      const float pivot = sp == 0 ? c.z : (sp == 1 ? c.w : d.x);                 // xc[sp], RCBForceTree.cxx:720
+      const int flag = split && recS[4 * p + sp] < pivot;                        // :640
+      const int head = split && i == off;
+      if (split) cmin = min(cmin, cl);
+      if (split && p == 0 && off < tile0) s_misc[q][0] = 1;
       const unsigned fb = __ballot_sync(0xffffffffu, flag), hb = __ballot_sync(0xffffffffu, head);
       if (lane == 0) {
         const int e = j * (PTPB / 32) + w;
@@ -612,6 +626,18 @@ __global__ void __launch_bounds__(PTPB + 32, PTPB == 256 ? 2 : 3) k_split_pass(c
   // round trips: with warp 0 doing it between the barriers the other warps stood waiting, 30 % of all stall samples), and
   // scans / publishes the A stage's entries behind the barrier.
   const bool helper = t >= PTPB;
+  // warp-collective, helper only: the number of left particles of tile k's first node in all earlier tiles, and the tile's
+  // inclusive word if it has not published one yet
+  auto resolve_carry = [&](int k) {
+    const int T = T00 + k * G, q = k % NST;
+    unsigned carry = 0;
+    if (s_misc[q][0]) {
+      carry = lookback<LB_W>(desc, T - 1, epoch, lane);
+      const int own = s_misc[q][3];
+      if (own >= 0 && lane == 0) desc_store(desc + T, desc_make(epoch, ST_PREFIX, carry + (unsigned)own));
+    }
+    if (lane == 0) s_misc[q][2] = (int)carry;
+  };
   if (helper && lane == 0) for (int k = 0; k < NST - 1; ++k) issue(k);
   if (!helper && nk > 0) stage_a(0);
   __syncthreads();
@@ -619,21 +645,21 @@ __global__ void __launch_bounds__(PTPB + 32, PTPB == 256 ? 2 : 3) k_split_pass(c
   __syncthreads();
   for (int k = 0; k < nk; ++k) {
     const int T0 = T00 + k * G, q = k % NST, tile0 = T0 * PT;
+    // The helper sums the look-back words of tile k while the workers run the A stage of tile k+1.  The words it needs were
+    // published an iteration ago, so it reads, it does not wait -- but it must not take longer than the A stage, or the
+    // workers stand at the barrier: one window of 32 words a round (LB_W = 1) measured 6.1 ms per build, two 6.2, four 6.7,
+    // eight 7.2 (21.5 M particles).  Doing the look-back a stage earlier, right behind the tile's own publication, is worse
+    // (7.5 ms): the neighbours' words of the same iteration are then not out yet and the helper spins on them.
+    if (helper) resolve_carry(k);
+    else if (k + 1 < nk) stage_a(k + 1);
+    __syncthreads();
+    // no barrier behind the scan: its results (and the published word) belong to tile k+1, which the workers touch in the next
+    // iteration; they go straight on with tile k, whose scan was made an iteration ago.  The bulk copies of tile k+NST-1 go
+    // into tile k-1's slot: every thread left it before the last barrier.
     if (helper) {
-      if (lane == 0) issue(k + NST - 1);      // its slot was tile k-1's: every thread left it before the last barrier
-      unsigned carry = 0;
-      if (s_misc[q][0]) {
-        carry = lookback<LB_W>(desc, T0 - 1, epoch, lane);
-        const int own = s_misc[q][3];
-        if (own >= 0 && lane == 0) desc_store(desc + T0, desc_make(epoch, ST_PREFIX, carry + (unsigned)own));
-      }
-      if (lane == 0) s_misc[q][2] = (int)carry;
-    } else if (k + 1 < nk) {
-      stage_a(k + 1);
+      if (k + 1 < nk) scan_publish(k + 1);
+      if (lane == 0) issue(k + NST - 1);
     }
-    __syncthreads();
-    if (helper && k + 1 < nk) scan_publish(k + 1);
-    __syncthreads();
     const int cbase = s_misc[q][1];          // in a register: the helper recycles the slot's words while the slots are flushed
     if (!helper) {
     // ---- B stage: destinations and stores ----------------------------------------------------------------------------------
@@ -714,11 +740,16 @@ __global__ void __launch_bounds__(PTPB + 32, PTPB == 256 ? 2 : 3) k_split_pass(c
           } else if (cl[j] > key) next = min(next, cl[j]);
         }
         const bool wl = __any_sync(0xffffffffu, anyl), wr = __any_sync(0xffffffffu, anyr);
+        int lm[4][3];        // warp sums of the 21-bit limbs of the four per-lane sums (|per-lane sum| < 2^52)
         if (wl) {
 #pragma unroll
           for (int qq = 0; qq < 3; ++qq) { bl[qq] = __reduce_min_sync(0xffffffffu, bl[qq]); bl[3 + qq] = __reduce_max_sync(0xffffffffu, bl[3 + qq]); }
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) s[qq] = warp_sum_ll(s[qq]);
+          for (int qq = 0; qq < 4; ++qq) {
+            lm[qq][0] = __reduce_add_sync(0xffffffffu, (int)(s[qq] & 0x1fffffll));
+            lm[qq][1] = __reduce_add_sync(0xffffffffu, (int)((s[qq] >> 21) & 0x1fffffll));
+            lm[qq][2] = __reduce_add_sync(0xffffffffu, (int)(s[qq] >> 42));
+          }
         }
         if (wr) {
 #pragma unroll
@@ -728,13 +759,13 @@ __global__ void __launch_bounds__(PTPB + 32, PTPB == 256 ? 2 : 3) k_split_pass(c
           const int sl2 = key - cbase;
           if (sl2 >= 0 && sl2 + 1 < NSLOT) {
             if (wl) {
-              Slot &S = slots[sl2];
+              PassSlot &S = slots[sl2];
               for (int qq = 0; qq < 3; ++qq) { atomicMin(&S.umin[qq], bl[qq]); atomicMax(&S.umax[qq], bl[3 + qq]); }
-              for (int qq = 0; qq < 4; ++qq) atomicAdd(&S.s[qq], (unsigned long long)s[qq]);
+              for (int qq = 0; qq < 4; ++qq) { atomicAdd(&S.limb[qq][0], lm[qq][0]); atomicAdd(&S.limb[qq][1], lm[qq][1]); atomicAdd(&S.limb[qq][2], lm[qq][2]); }
               S.used = 1;
             }
             if (wr) {
-              Slot &S = slots[sl2 + 1];
+              PassSlot &S = slots[sl2 + 1];
               for (int qq = 0; qq < 3; ++qq) { atomicMin(&S.umin[qq], br[qq]); atomicMax(&S.umax[qq], br[3 + qq]); }
               S.used = 1;
             }
@@ -742,7 +773,8 @@ __global__ void __launch_bounds__(PTPB + 32, PTPB == 256 ? 2 : 3) k_split_pass(c
             if (wl) {
               NodeAcc &A = acc[key];
               for (int qq = 0; qq < 3; ++qq) { atomicMin(&A.umin[qq], bl[qq]); atomicMax(&A.umax[qq], bl[3 + qq]); }
-              for (int qq = 0; qq < 4; ++qq) add_split(&A.lo[qq], &A.hi[qq], s[qq]);
+              for (int qq = 0; qq < 4; ++qq)
+                add_split(&A.lo[qq], &A.hi[qq], (long long)lm[qq][0] + ((long long)lm[qq][1] << 21) + ((long long)lm[qq][2] << 42));
             }
             if (wr) {
               NodeAcc &A = acc[key + 1];
@@ -757,10 +789,11 @@ __global__ void __launch_bounds__(PTPB + 32, PTPB == 256 ? 2 : 3) k_split_pass(c
     __syncthreads();
     if (t < NSLOT && slots[t].used) {
       NodeAcc &A = acc[cbase + t];
-      Slot &S = slots[t];
+      PassSlot &S = slots[t];
       for (int qq = 0; qq < 3; ++qq) { atomicMin(&A.umin[qq], S.umin[qq]); atomicMax(&A.umax[qq], S.umax[qq]); }
-      for (int qq = 0; qq < 4; ++qq) add_split(&A.lo[qq], &A.hi[qq], (long long)S.s[qq]);
-      slot_reset(S);
+      for (int qq = 0; qq < 4; ++qq)
+        add_split(&A.lo[qq], &A.hi[qq], (long long)S.limb[qq][0] + ((long long)S.limb[qq][1] << 21) + ((long long)S.limb[qq][2] << 42));
+      pslot_reset(S);
     }
   }
 }

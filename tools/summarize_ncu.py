@@ -23,6 +23,10 @@ METRICS = [
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__inst_executed.sum",
 ]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 
@@ -33,7 +37,10 @@ def load(path):
     else:
         out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     out = "\n".join(l for l in out.splitlines() if l.startswith('"'))
-    rows = list(csv.reader(io.StringIO(out)))
+    # ncu 2025.2 writes an empty record after every launch and prefixes some metric names with their section
+    # ("FBSP.TriageCompute.dram__..."): keep the full-width rows only (the empty ones made every later column of
+    # k_force_rem read as NaN in round 1) and address metrics by their suffix
+    rows = [r for r in csv.reader(io.StringIO(out)) if len(r) > 20]
     return rows[0], rows[1], rows[2:]
 
 
@@ -49,6 +56,11 @@ def main():
     a = ap.parse_args()
     hdr, units, rows = load(a.report)
     col = {h: i for i, h in enumerate(hdr)}
+    for i, h in enumerate(hdr):          # suffix aliases: "SECTION.metric" -> "metric" (first occurrence wins)
+        if "." in h:
+            for cut in range(1, h.count(".") + 1):
+                tail = h.split(".", cut)[-1]
+                col.setdefault(tail, i)
     groups = collections.OrderedDict()
     for r in rows:
         groups.setdefault(short(r[col["Kernel Name"]]), []).append(r)
