@@ -69,7 +69,7 @@ def parse():
                     "by default culling is off and only a side measurement of it is reported under 'culled'")
     ap.add_argument("--no-refresh-block", action="store_true",
                     help="skip the side block 'refresh' (overload refresh of one global snapshot decomposed over the ranks, configs[3])")
-    ap.add_argument("--tune-ppn", default="128,256", help="comma-separated leaf sizes for the side block 'tuned' (time to solution per "
+    ap.add_argument("--tune-ppn", default="64,128,256", help="comma-separated leaf sizes for the side block 'tuned' (time to solution per "
                     "kick at other -N than the reference's shipped 512; '' = skip)")
     return ap.parse_args()
 
@@ -472,7 +472,14 @@ class Bench:
             ks = [self.kick(ppn=ppn) for _ in range(3)]
             kc = self.kick(ppn=ppn, count_in_cutoff=True)
             ms = float(np.mean([k["ms_total"] for k in ks])); msf = float(np.mean([k["ms_force"] for k in ks]))
-            rows.append({"ppn": ppn, "ms_kick": ms, "ms_force": msf, "ms_build": float(np.mean([k["ms_build"] for k in ks])),
+            ms_cull = None
+            if self.args.arith != "x86":
+                self.g.set_culling(not self.args.cull)
+                self.kick(ppn=ppn)
+                ms_cull = float(np.mean([self.kick(ppn=ppn)["ms_total"] for _ in range(3)]))
+                self.g.set_culling(self.args.cull)
+            rows.append({"ppn": ppn, "ms_kick": ms, "ms_kick_culling_%s" % ("off" if self.args.cull else "on"): ms_cull,
+                         "ms_force": msf, "ms_build": float(np.mean([k["ms_build"] for k in ks])),
                          "pairs_evaluated": int(kc["pairs_evaluated"]), "pairs_in_cutoff": int(kc["pairs_in_cutoff"]),
                          "in_cutoff_Gpairs_per_s": kc["pairs_in_cutoff"] / (ms * 1e-3) / 1e9,
                          "roofline_frac": FLOP_PER_PAIR * kc["pairs_evaluated"] / (msf * 1e-3) / 1e12 / self.fp32_peak,

@@ -80,7 +80,8 @@ def check_accel(out, o, o64, og, tag="", of=None):
     would.  Those particles are identified on the CPU (oracle fused vs oracle generic), counted and bounded; every other
     particle meets the same 1e-5 * G_i gate against the x86 reference, and EVERY particle meets it against the oracle's
     restatement of the fused arithmetic.  MUFU.RSQ(s) cubed carries 3x the relative error of rsqrt(s^3), so the distance
-    to the FP64 sum is allowed 4x the CPU's instead of 1.25x (measured 3.2x; about 1e-6 of |a| in the median)."""
+    to the FP64 sum is allowed 4x the CPU's instead of 1.25x on these small cases (up to 3.2x seen in their tail quantiles, which are
+    a handful of particles; at full size the ratio is 1.06-1.23 and tests/test_gpu_fullsize.py asserts <= 1.25 in the median)."""
     a, b, c = by_id(out), by_id(o), by_id(o64)
     gross = np.maximum(by_id(og)["vx"].astype(np.float64), 1e-30)
     d = _dist(a, b)

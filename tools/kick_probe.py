@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Two full kicks (build + walk + force) on the bench snapshot, for profiler captures: the second kick is the warm one.
+"""Three full kicks (build + walk + force) on the bench snapshot, for profiler captures of the second one.
     python tools/kick_probe.py [uniform|clustered] [np_side] [ppn] [fused|x86|fused_rs3] [cull]"""
 import os
 import sys
@@ -20,7 +20,7 @@ g.set_force_law(H.LAW_SR_POLY, H.POLY5, 0.007, H.RMAX)
 g.set_culling(len(sys.argv) > 5 and sys.argv[5] == "cull")
 g.upload(p)
 b = ([0.0] * 3, [float(nglt)] * 3, [3.2] * 3, [nglt - 3.2] * 3)
-for _ in range(2):
+for _ in range(3):          # a profiler capture takes the second kick: warm, and not the last work of the process
     st = g.kick(*b, 0.5, ppn)
 print("%s side=%d ppn=%d: build %.3f walk %.3f force %.3f ms, %d levels, %d launches" % (
     state, side, ppn, st["ms_build"], st["ms_walk"], st["ms_force"], st["levels"], st["total_launches"]))

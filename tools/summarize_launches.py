@@ -12,10 +12,10 @@ from collections import OrderedDict
 
 
 def short(name):
-    m = re.search(r"haccsr::(\w+)", name)
+    # ncu prints libhaccsr's kernels with or without their namespace, depending on the version
+    m = re.match(r"(?:void )?(?:haccsr::)?(k_\w+)(<[^>]*>)?", name)
     if m:
-        t = re.search(r"haccsr::\w+<([^>]*)>", name)
-        return m.group(1) + ("<" + t.group(1) + ">" if t else ""), True
+        return m.group(1) + (m.group(2) or ""), True
     return re.sub(r"\(.*", "", name)[:60], False
 
 
