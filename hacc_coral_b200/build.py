@@ -6,7 +6,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 HOST = os.path.join(_HERE, "host")
-SOURCES = ["api.cu", "tree_build.cu", "walk.cu", "force.cu", "refresh.cu", "exchange.cu", "cic.cu"]
+SOURCES = ["api.cu", "tree_build.cu", "walk.cu", "force.cu", "force_v0.cu", "force_v1.cu", "force_v2.cu", "force_v3.cu", "force_v4.cu",
+           "refresh.cu", "exchange.cu", "cic.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -28,7 +29,7 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     """Compile csrc/*.cu -> csrc/libhaccsr.so and host/RCBForceTree.cxx -> host/libhaccsr_facade.so."""
     out = os.path.join(CSRC, "libhaccsr.so")
-    common = [os.path.join(CSRC, "common.cuh"), os.path.join(_HERE, "..", "include", "haccsr.h")]
+    common = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "force_kernels.cuh"), os.path.join(_HERE, "..", "include", "haccsr.h")]
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     # one object per source, compiled in parallel and only when stale (force.cu alone takes minutes: 5 arithmetic variants)

@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(PTPB + 32, PTPB == 256 ? 2 : 3) k_split_pass(c
   __shared__ unsigned long long s_bar[NST];
   __shared__ PassSlot slots[NSLOT];
   if (st->error || (level > 0 && st->nsplit[level - 1] <= 0)) return;     // the tree was finished by an earlier pass
+  if (st->nsplit[level] == 0) return;      // no node splits at this level: its leaves are finalised by k_gather, from these buffers
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const unsigned epoch = (unsigned)level + 1u;
   const unsigned below = (1u << lane) - 1u;
@@ -968,14 +969,34 @@ __global__ void __launch_bounds__(128) k_pp12_internal(const Node *__restrict__ 
 }
 
 // ---- permute the caller-visible arrays into tree order (the reference does this in place, :648-669) ------
-__global__ void __launch_bounds__(256) k_gather(Soa in, Soa out, const float4 *__restrict__ src4,
-                                                const unsigned *__restrict__ perm, int n) {
+// Also the last level's "pass": at the level where no node splits any more, every particle that is not final yet belongs to a
+// leaf (or to an orphan holding a degenerate node's particles) and only has to be written to its final place -- mirrored if
+// the leaf is a reversed one (k_split_pass) -- so the split pass skips that level and the gather takes those particles
+// straight from the level's record buffers: one pass over the particles less.
+__global__ void __launch_bounds__(256) k_gather(Soa in, Soa out, float4 *__restrict__ src4, const unsigned *__restrict__ perm,
+                                                const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
+                                                const int *__restrict__ nid, const Node *__restrict__ nodes, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    unsigned p = perm[i];
-    float4 r = src4[i];
-    out.x[i] = r.x; out.y[i] = r.y; out.z[i] = r.z; out.mass[i] = r.w;
-    out.vx[i] = in.vx[p]; out.vy[i] = in.vy[p]; out.vz[i] = in.vz[p];
-    out.phi[i] = in.phi[p]; out.id[i] = in.id[p]; out.mask[i] = in.mask[p];
+    const int nd = nid[i];
+    unsigned p;
+    float4 r;
+    int fin = i;
+    if (nd < 0) {
+      p = perm[i]; r = src4[i];
+    } else {
+      p = idx[i]; r = rec[i];
+      const float4 *np = reinterpret_cast<const float4 *>(nodes + nd);
+      const float4 d = __ldg(np + 3);
+      if (__float_as_int(d.w) == -2) {
+        float4 a = __ldg(np);
+        if (__float_as_int(a.x) == 0) a = __ldg(reinterpret_cast<const float4 *>(nodes + __float_as_int(d.z)));   // orphan: the parent's range
+        fin = 2 * __float_as_int(a.y) + __float_as_int(a.x) - 1 - i;
+      }
+      src4[fin] = r;
+    }
+    out.x[fin] = r.x; out.y[fin] = r.y; out.z[fin] = r.z; out.mass[fin] = r.w;
+    out.vx[fin] = in.vx[p]; out.vy[fin] = in.vy[p]; out.vz[fin] = in.vz[p];
+    out.phi[fin] = in.phi[p]; out.id[fin] = in.id[p]; out.mask[fin] = in.mask[p];
   }
 }
 
@@ -1175,6 +1196,17 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
       for (int L = 0; L < n_levels; ++L) { c->level_begin[L] = S.lvl_begin[L]; c->level_end[L] = S.lvl_end[L]; }
     }
     const int nnodes = c->n_nodes;
+    {
+      // the record buffers the last level read from: level L reads A if L is even
+      const bool even = ((c->n_levels - 1) & 1) == 0;
+      const float4 *lrec = even ? c->recA.p : c->recB.p;
+      const unsigned *lidx = even ? c->idxA.p : c->idxB.p;
+      const int *lnid = even ? c->nidA.p : c->nidB.p;
+      if (c->wait_up2) { HSR_CUDA(cudaStreamWaitEvent(st, c->ev_up2, 0)); c->wait_up2 = false; }
+      k_gather<<<grid_lin, 256, 0, st>>>(c->cur, c->alt, c->src4.p, c->perm.p, lrec, lidx, lnid, c->nodes.p, n);
+      c->launches++;
+      HSR_CUDA(cudaGetLastError());
+    }
     for (int L = c->n_levels - 2; L >= 0; --L) {
       int nl = c->level_end[L] - c->level_begin[L];
       k_moments<<<(nl + 255) / 256, 256, 0, st>>>(c->nodes.p, c->src4.p, c->level_begin[L], c->level_end[L]);
@@ -1196,10 +1228,6 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
       }
       HSR_CUDA(cudaGetLastError());
     }
-    if (c->wait_up2) { HSR_CUDA(cudaStreamWaitEvent(st, c->ev_up2, 0)); c->wait_up2 = false; }
-    k_gather<<<grid_lin, 256, 0, st>>>(c->cur, c->alt, c->src4.p, c->perm.p, n);
-    c->launches++;
-    HSR_CUDA(cudaGetLastError());
     // particles beyond n (out-of-box tail) keep their place: copy them across so cur/alt can be swapped
     if (c->n_resident > n) {
       size_t m = (size_t)(c->n_resident - n);
