@@ -20,7 +20,7 @@ import pytest
 
 import hacc_coral_b200 as H
 from hacc_coral_b200 import synth
-from tests.util import EDGE, RSM, THETA, accel_errors, boxes, by_id, compare_trees
+from tests.util import EDGE, RSM, THETA, accel_errors, boxes, by_id, compare_trees, tree_key_map
 
 pytestmark = pytest.mark.gpu
 
@@ -728,3 +728,25 @@ def test_tuned_leaf_size_against_reference_at_512(oracle, ppn):
     assert (d[inside] / gross[inside]).max() <= 1e-5                               # ... the same kicks
     rel, _, _, _ = accel_errors({k: a[k][inside] for k in ("vx", "vy", "vz")}, {k: r[k][inside] for k in ("vx", "vy", "vz")})
     assert np.median(rel) <= 5e-6 and np.quantile(rel, 0.99) <= 1e-4
+
+
+def test_particles_outside_the_tree_box_and_large_masses(oracle):
+    """The caller's tree box is only the root's initial box: the reference replaces it by the tight box at once
+    (RCBForceTree.cxx:785-786), so nothing requires the particles to lie inside it, and the fixed-point scale of the exact centroid
+    sums must come from the particles, not from the box.  Particles far outside the box and masses up to 30: the reference's
+    tree (ranges, boxes, centroids, leaf members bit for bit; the monopole masses are float sums in a different order: 1e-6)."""
+    p = synth.clustered(30000, 40.0, seed=31)
+    rng = np.random.default_rng(32)
+    p["mass"] = (0.25 + 30.0 * rng.random(p["x"].size)).astype(np.float32)
+    small = ([0.0] * 3, [4.0] * 3, [3.2] * 3, [36.8] * 3)          # tree box far smaller than the particle cloud
+    for b in (small, boxes(40)):
+        out, st, tree, _ = gpu_run(p, b, 0.5, 64, arith=H.ARITH_X86)
+        o = oracle.run(p, *b, RSM, 0.5, 64, form=oracle.FORM_GENERIC)
+        assert st["nodes"] == o["stats"]["nodes"] and st["pairs_evaluated"] == o["stats"]["pairs_eval"]
+        cmp = compare_trees(o["tree"], o["id"], tree, out["id"])
+        for k in ("missing", "box_mismatch", "xc_mismatch", "leaf_flag_mismatch", "leaf_members_mismatch"):
+            assert cmp[k] == 0, (k, cmp)
+        ka, kb = tree_key_map(o["tree"]), tree_key_map(tree)
+        ia = np.array([ka[k] for k in ka if k[1] > 1]); ib = np.array([kb[k] for k in ka if k[1] > 1])
+        pa, pb = o["tree"]["ppm"][ia].astype(np.float64), tree["ppm"][ib].astype(np.float64)
+        assert np.all(np.abs(pa - pb) <= 2e-6 * np.abs(pa))
