@@ -154,8 +154,15 @@ int haccsr_create(haccsr_ctx **out, int device, int64_t max_particles) {
     if (cudaMalloc((void **)&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) { rc = 2; break; }
     if (cudaMalloc((void **)&c->d_slotcount, 32 * sizeof(long long)) != cudaSuccess) { rc = 2; break; }
     for (int i = 0; i < 5; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { rc = 2; break; }
-    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = 2; break; }
+    {
+      // the copy stream also runs the small gather of phi / id / mask while the force kernel (130 k one-warp CTAs) owns the
+      // machine: with equal priority its blocks queue behind the force kernel's and the downloads behind it start late
+      int least = 0, greatest = 0;
+      if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { rc = 2; break; }
+      if (cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, greatest) != cudaSuccess) { rc = 2; break; }
+    }
     if (cudaEventCreateWithFlags(&c->ev_up2, cudaEventDisableTiming) != cudaSuccess) { rc = 2; break; }
+    if (cudaEventCreateWithFlags(&c->ev_vready, cudaEventDisableTiming) != cudaSuccess) { rc = 2; break; }
     if (cudaEventCreateWithFlags(&c->ev_built, cudaEventDisableTiming) != cudaSuccess) { rc = 2; break; }
     { bool bad = false;
       for (int g = 0; g < 8; ++g) if (cudaEventCreateWithFlags(&c->ev_grp[g], cudaEventDisableTiming) != cudaSuccess) bad = true;
@@ -190,6 +197,8 @@ int haccsr_destroy(haccsr_ctx *c) {
   c->refresh_cand.release(); c->xchg_send.release(); c->xchg_recv.release(); c->xchg_table.release();
   for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->ev_up2) cudaEventDestroy(c->ev_up2);
+  if (c->ev_vready) cudaEventDestroy(c->ev_vready);
+  for (int q = 0; q < 3; ++q) c->kick_a[q].release();
   if (c->ev_built) cudaEventDestroy(c->ev_built);
   for (int g = 0; g < 8; ++g) if (c->ev_grp[g]) cudaEventDestroy(c->ev_grp[g]);
   if (c->ev_main) cudaEventDestroy(c->ev_main);
@@ -337,6 +346,11 @@ int issue_host_out(haccsr_ctx *c) {
   const size_t fb = (size_t)count * sizeof(float);
   HSR_CUDA(cudaEventRecord(c->ev_built, s));
   HSR_CUDA(cudaStreamWaitEvent(cs, c->ev_built, 0));
+  // velocities, phi, id, mask into tree order: behind their upload (same stream) and behind the build.  The build and the force
+  // kernel do not wait for any of them: the force kernel leaves accelerations and apply_kick() kicks behind ev_vready (with
+  // eight ranks sharing one host the six arrays take 33 ms to arrive, which used to sit between the build and the force kernel)
+  HSR_TRY(gather_payload(c, cs));
+  HSR_CUDA(cudaEventRecord(c->ev_vready, cs));
   HSR_CUDA(cudaMemcpyAsync(ho->x, c->cur.x, fb, cudaMemcpyDeviceToHost, cs));
   HSR_CUDA(cudaMemcpyAsync(ho->y, c->cur.y, fb, cudaMemcpyDeviceToHost, cs));
   HSR_CUDA(cudaMemcpyAsync(ho->z, c->cur.z, fb, cudaMemcpyDeviceToHost, cs));
@@ -376,6 +390,7 @@ static int kick_impl(haccsr_ctx *c, int64_t count, const float tree_lo[3], const
   // waits in the same copy engine (measured: the walk took 11.8 ms instead of 0.7 ms).
   c->pending_ho = ho ? (const void *)ho : nullptr;
   c->pending_count = count;
+  c->defer_kick = ho != nullptr;
   HSR_TRY(build_lists(c, force_lo, force_hi, theta, st));
   HSR_CUDA(cudaEventRecord(c->ev[2], s));
   if (!skip_force) {
@@ -401,6 +416,7 @@ static int kick_impl(haccsr_ctx *c, int64_t count, const float tree_lo[3], const
     HSR_CUDA(cudaEventRecord(c->ev[3], s));
     if (ho && !copied) {
       const size_t fb = (size_t)count * sizeof(float);
+      HSR_CUDA(cudaStreamWaitEvent(s, c->ev_vready, 0));       // the velocities are permuted on the copy stream
       HSR_CUDA(cudaMemcpyAsync(ho->vx, c->cur.vx, fb, cudaMemcpyDeviceToHost, s));
       HSR_CUDA(cudaMemcpyAsync(ho->vy, c->cur.vy, fb, cudaMemcpyDeviceToHost, s));
       HSR_CUDA(cudaMemcpyAsync(ho->vz, c->cur.vz, fb, cudaMemcpyDeviceToHost, s));
@@ -409,6 +425,7 @@ static int kick_impl(haccsr_ctx *c, int64_t count, const float tree_lo[3], const
     HSR_TRY(issue_host_out(c));
     HSR_CUDA(cudaEventRecord(c->ev[3], s));
   }
+  c->defer_kick = false;
   if (ho) HSR_CUDA(cudaStreamSynchronize(c->copy_stream));
   HSR_CUDA(cudaStreamSynchronize(s));
   HSR_CUDA(cudaGetLastError());

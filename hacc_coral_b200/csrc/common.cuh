@@ -178,7 +178,9 @@ struct haccsr_ctx {
   haccsr::DevBuf<unsigned char> xchg_send, xchg_recv;   // haccsr_refresh: packed messages out / in
   haccsr::DevBuf<long long> xchg_table;      // haccsr_refresh: gathered count table, append table
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_up2 = nullptr, ev_built = nullptr, ev_main = nullptr;
+  cudaEvent_t ev_up2 = nullptr, ev_vready = nullptr, ev_built = nullptr, ev_main = nullptr;   // ev_up2: all uploads done; ev_vready: velocities in tree order
+  bool defer_kick = false;            // haccsr_kick_host: the force kernel stores accelerations, apply_kick() kicks (force.cu)
+  haccsr::DevBuf<float> kick_a[3];    // those accelerations
   bool wait_up2 = false;    // build_tree must wait for ev_up2 before it permutes the payload arrays
   // haccsr_kick_host: the force kernel runs as `force_groups` launches by particle range and the velocities of each
   // range go to the host arrays ho_v on the copy stream as soon as they are final (force.cu)
@@ -201,6 +203,10 @@ int build_tree(haccsr_ctx *c, int64_t n, const float lo[3], const float hi[3], i
 int build_lists(haccsr_ctx *c, const float flo[3], const float fhi[3], float theta, haccsr_stats *st);
 // force.cu
 int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *st);
+// tree_build.cu: phi / id / mask into tree order by the completed permutation (second part of the split gather)
+int gather_payload(haccsr_ctx *c, cudaStream_t st);
+// force.cu: v = fma(fcoeff * m, a, v) for particles [lo, hi) from the deferred accelerations
+int apply_kick(haccsr_ctx *c, float fcoeff, int64_t lo, int64_t hi);
 // api.cu: queue the device->host copies of the seven arrays the force kernel does not write (haccsr_kick_host)
 int issue_host_out(haccsr_ctx *c);
 // api.cu: stable two-way partition of the ten arrays by a 0/1 flag

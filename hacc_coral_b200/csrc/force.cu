@@ -104,6 +104,31 @@ __global__ void k_lpt_scatter(const WorkItem *__restrict__ items, const unsigned
   out[atomicAdd(&cursor[lpt_bin(w, list_len, G)], 1u)] = w;
 }
 
+__global__ void __launch_bounds__(256) k_apply_kick(float *__restrict__ vx, float *__restrict__ vy, float *__restrict__ vz,
+                                                    const float *__restrict__ ax, const float *__restrict__ ay,
+                                                    const float *__restrict__ az, const float4 *__restrict__ src4, float fcoeff,
+                                                    long long lo, long long hi) {
+  for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+    const float a = ax[i];
+    if (a != a) continue;                                    // not a sink
+    const float c = fcoeff * __ldg(&src4[i].w);              // kick: v += fcoeff * m_i * a   (RCBForceTree.cxx:594-596 / :615-617)
+    vx[i] = fmaf(c, a, vx[i]); vy[i] = fmaf(c, ay[i], vy[i]); vz[i] = fmaf(c, az[i], vz[i]);
+  }
+}
+
+// deferred kick of particles [lo, hi): waits for the velocities to have been permuted into tree order on the copy stream
+int apply_kick(haccsr_ctx *c, float fcoeff, int64_t lo, int64_t hi) {
+  if (hi <= lo) return 0;
+  HSR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_vready, 0));
+  int64_t g = (hi - lo + 255) / 256;
+  if (g > (int64_t)c->sm_count * 16) g = (int64_t)c->sm_count * 16;
+  k_apply_kick<<<(int)g, 256, 0, c->stream>>>(c->cur.vx, c->cur.vy, c->cur.vz, c->kick_a[0].p, c->kick_a[1].p, c->kick_a[2].p,
+                                              c->src4.p, fcoeff, (long long)lo, (long long)hi);
+  c->launches++;
+  HSR_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *st) {
   cudaStream_t s = c->stream;
   const int nn = c->n_nodes;
@@ -149,6 +174,19 @@ int run_force(haccsr_ctx *c, float fcoeff, bool count_in_cutoff, haccsr_stats *s
   P.items = c->items_sorted.p; P.range_off = c->range_off.p; P.ranges = c->ranges.p; P.list_len = c->list_len.p;
   P.src4 = c->src4.p; P.pool = c->pool.p;
   P.vx = c->cur.vx; P.vy = c->cur.vy; P.vz = c->cur.vz;
+  P.defer = 0;
+  if (c->defer_kick) {
+    // haccsr_kick_host: the velocities arrive (and are permuted) while the force kernel runs, so it leaves the accelerations in
+    // arrays of their own and apply_kick() does v = fma(fcoeff * m, a, v) range by range -- the same operation, the same bits.
+    // NaN marks "not a sink": particles of leaves outside the force box keep their velocity untouched.
+    const size_t nn = (size_t)c->n_tree + 1;
+    for (int q = 0; q < 3; ++q) {
+      HSR_TRY(c->kick_a[q].ensure(nn));
+      HSR_CUDA(cudaMemsetAsync(c->kick_a[q].p, 0xff, nn * sizeof(float), s));
+    }
+    P.vx = c->kick_a[0].p; P.vy = c->kick_a[1].p; P.vz = c->kick_a[2].p;
+    P.defer = 1;
+  }
   P.incut = c->d_counters + 11;
   for (int i = 0; i < 8; ++i) { P.a[i] = c->law.a[i]; P.b[i] = -c->law.b[i]; }
   P.rsm2 = c->law.rsm2; P.rmax2 = c->law.rmax2; P.smax = c->law.smax; P.fcoeff = fcoeff;

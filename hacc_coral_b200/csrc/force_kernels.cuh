@@ -48,6 +48,7 @@ struct ForceParams {
   float b[8];                  // SR_POLY, fused arithmetic: MINUS the polynomial re-expanded in s = r2 + rsm^2
   float rsm2, rmax2, smax, fcoeff;   // smax = rmax2 + rsm2: the cutoff on s
   int unit_mass;               // 1: every particle mass is exactly 1.0f
+  int defer;                   // 1: vx vy vz point at acceleration arrays; the kernel stores a_i there and apply_kick() kicks later
   const float *tab_f, *tab_r2; // SR_INTERP: grid force and its abscissae r2_i (device arrays of ntab floats)
   float tab_r2min, tab_r2max, tab_oodr2;
   int ntab;
@@ -391,6 +392,7 @@ __device__ __forceinline__ void run_item(const WorkItem it, const ForceParams &P
         ax = (g & 1) ? k.ax.y : k.ax.x; ay = (g & 1) ? k.ay.y : k.ay.x; az = (g & 1) ? k.az.y : k.az.x;
       } else { const SinkRegs1 &k = k1[g - 2 * S2]; ax = k.ax; ay = k.ay; az = k.az; }
       int gi = node_off_sink + j;
+      if (P.defer) { P.vx[gi] = ax; P.vy[gi] = ay; P.vz[gi] = az; continue; }     // haccsr_kick_host: the velocities are still on their way
       float c = P.fcoeff * __ldg(&P.src4[gi].w);
       P.vx[gi] = fmaf(c, ax, P.vx[gi]); P.vy[gi] = fmaf(c, ay, P.vy[gi]); P.vz[gi] = fmaf(c, az, P.vz[gi]);
     }
@@ -525,8 +527,12 @@ __device__ __forceinline__ void run_item_rem(const WorkItem it, const ForceParam
     const int j = b * REM_SINKS + lane;
     if (lane < REM_SINKS && j < it.sink_count) {
       const int gi = it.sink_begin + j;
-      const float c = P.fcoeff * __ldg(&P.src4[gi].w);
-      P.vx[gi] = fmaf(c, ax, P.vx[gi]); P.vy[gi] = fmaf(c, ay, P.vy[gi]); P.vz[gi] = fmaf(c, az, P.vz[gi]);
+      if (P.defer) {
+        P.vx[gi] = ax; P.vy[gi] = ay; P.vz[gi] = az;
+      } else {
+        const float c = P.fcoeff * __ldg(&P.src4[gi].w);
+        P.vx[gi] = fmaf(c, ax, P.vx[gi]); P.vy[gi] = fmaf(c, ay, P.vy[gi]); P.vz[gi] = fmaf(c, az, P.vz[gi]);
+      }
     }
     if (COUNT) {
 #pragma unroll
@@ -641,6 +647,7 @@ int launch_force(haccsr_ctx *c, const ForceParams &P0, int n_items, bool count) 
       if (!rem) c->force_launches++;     // haccsr_stats::force_launches counts the groups (k_force launches)
       HSR_CUDA(cudaGetLastError());
     }
+    if (P0.defer) HSR_TRY(apply_kick(c, P0.fcoeff, c->group_lo[g], c->group_lo[g + 1]));
     if (groups > 1 && c->ho_v[0]) {
       // velocities of particles [lo, hi) are final once every launch up to this one is done
       const int64_t lo = c->group_lo[g], hi = c->group_lo[g + 1];

@@ -973,31 +973,56 @@ __global__ void __launch_bounds__(128) k_pp12_internal(const Node *__restrict__ 
 // leaf (or to an orphan holding a degenerate node's particles) and only has to be written to its final place -- mirrored if
 // the leaf is a reversed one (k_split_pass) -- so the split pass skips that level and the gather takes those particles
 // straight from the level's record buffers: one pass over the particles less.
-__global__ void __launch_bounds__(256) k_gather(Soa in, Soa out, float4 *__restrict__ src4, const unsigned *__restrict__ perm,
+// PART bit 0: positions and mass (what the walk and the force kernel read); also completes src4 / perm for the last level's
+// leaves.  Bit 1: phi, id, mask; bit 2: velocities.  haccsr_kick (resident particles) does all three at once; haccsr_kick_host
+// runs part 1 in the build and parts 2 + 4 later on its copy stream, from the completed permutation: they wait for the upload
+// of arrays the build does not read, and must not hold it up (api.cu).
+template <int PART>
+__global__ void __launch_bounds__(256) k_gather(Soa in, Soa out, float4 *__restrict__ src4, unsigned *__restrict__ perm,
                                                 const float4 *__restrict__ rec, const unsigned *__restrict__ idx,
                                                 const int *__restrict__ nid, const Node *__restrict__ nodes, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int nd = nid[i];
-    unsigned p;
-    float4 r;
-    int fin = i;
-    if (nd < 0) {
-      p = perm[i]; r = src4[i];
-    } else {
-      p = idx[i]; r = rec[i];
-      const float4 *np = reinterpret_cast<const float4 *>(nodes + nd);
-      const float4 d = __ldg(np + 3);
-      if (__float_as_int(d.w) == -2) {
-        float4 a = __ldg(np);
-        if (__float_as_int(a.x) == 0) a = __ldg(reinterpret_cast<const float4 *>(nodes + __float_as_int(d.z)));   // orphan: the parent's range
-        fin = 2 * __float_as_int(a.y) + __float_as_int(a.x) - 1 - i;
+    if (PART & 1) {
+      const int nd = nid[i];
+      unsigned p;
+      float4 r;
+      int fin = i;
+      if (nd < 0) {
+        p = perm[i]; r = src4[i];
+      } else {
+        p = idx[i]; r = rec[i];
+        const float4 *np = reinterpret_cast<const float4 *>(nodes + nd);
+        const float4 d = __ldg(np + 3);
+        if (__float_as_int(d.w) == -2) {
+          float4 a = __ldg(np);
+          if (__float_as_int(a.x) == 0) a = __ldg(reinterpret_cast<const float4 *>(nodes + __float_as_int(d.z)));   // orphan: the parent's range
+          fin = 2 * __float_as_int(a.y) + __float_as_int(a.x) - 1 - i;
+        }
+        src4[fin] = r;
+        if (PART != 7) perm[fin] = p;       // the other parts run later, from the completed permutation
       }
-      src4[fin] = r;
+      out.x[fin] = r.x; out.y[fin] = r.y; out.z[fin] = r.z; out.mass[fin] = r.w;
+      if (PART & 4) { out.vx[fin] = in.vx[p]; out.vy[fin] = in.vy[p]; out.vz[fin] = in.vz[p]; }
+      if (PART & 2) { out.phi[fin] = in.phi[p]; out.id[fin] = in.id[p]; out.mask[fin] = in.mask[p]; }
+    } else {
+      const unsigned p = perm[i];
+      if (PART & 4) { out.vx[i] = in.vx[p]; out.vy[i] = in.vy[p]; out.vz[i] = in.vz[p]; }
+      if (PART & 2) { out.phi[i] = in.phi[p]; out.id[i] = in.id[p]; out.mask[i] = in.mask[p]; }
     }
-    out.x[fin] = r.x; out.y[fin] = r.y; out.z[fin] = r.z; out.mass[fin] = r.w;
-    out.vx[fin] = in.vx[p]; out.vy[fin] = in.vy[p]; out.vz[fin] = in.vz[p];
-    out.phi[fin] = in.phi[p]; out.id[fin] = in.id[p]; out.mask[fin] = in.mask[p];
   }
+}
+
+// the later parts of the split gather (velocities, phi, id, mask), queued by haccsr_kick_host on its copy stream behind the uploads
+int gather_payload(haccsr_ctx *c, cudaStream_t st) {
+  const int n = (int)c->n_tree;
+  if (n <= 0) return 0;
+  int grid_lin = (n + TPB - 1) / TPB;
+  if (grid_lin > c->sm_count * 16) grid_lin = c->sm_count * 16;
+  // build_tree has swapped the two array sets: `alt` is the upload, `cur` the tree-ordered set
+  k_gather<6><<<grid_lin, 256, 0, st>>>(c->alt, c->cur, c->src4.p, c->perm.p, nullptr, nullptr, nullptr, c->nodes.p, n);
+  c->launches++;
+  HSR_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ---- host orchestration -------------------------------------------------------------------------------
@@ -1202,8 +1227,14 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
       const float4 *lrec = even ? c->recA.p : c->recB.p;
       const unsigned *lidx = even ? c->idxA.p : c->idxB.p;
       const int *lnid = even ? c->nidA.p : c->nidB.p;
-      if (c->wait_up2) { HSR_CUDA(cudaStreamWaitEvent(st, c->ev_up2, 0)); c->wait_up2 = false; }
-      k_gather<<<grid_lin, 256, 0, st>>>(c->cur, c->alt, c->src4.p, c->perm.p, lrec, lidx, lnid, c->nodes.p, n);
+      if (c->wait_up2) {
+        // haccsr_kick_host: positions only, nothing to wait for; the six arrays still on their way are permuted on the copy
+        // stream (gather_payload) and the kick itself is deferred (force.cu: apply_kick)
+        c->wait_up2 = false;
+        k_gather<1><<<grid_lin, 256, 0, st>>>(c->cur, c->alt, c->src4.p, c->perm.p, lrec, lidx, lnid, c->nodes.p, n);
+      } else {
+        k_gather<7><<<grid_lin, 256, 0, st>>>(c->cur, c->alt, c->src4.p, c->perm.p, lrec, lidx, lnid, c->nodes.p, n);
+      }
       c->launches++;
       HSR_CUDA(cudaGetLastError());
     }
