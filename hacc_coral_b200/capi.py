@@ -106,6 +106,7 @@ def load_library():
     lib.haccsr_refresh_pack.argtypes = [vp, ip64, vp]
     lib.haccsr_refresh_append.argtypes = [vp, vp, C.c_int64]
     lib.haccsr_refresh.argtypes = [vp, vp, i32p, C.c_int32, fp, fp, C.c_float, C.POINTER(RefreshStats)]
+    lib.haccsr_refresh_plan.argtypes = [i32p, C.c_int32, i32p, i32p]
     lib.haccsr_nccl_unique_id.argtypes = [vp]
     lib.haccsr_nccl_comm_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp]
     lib.haccsr_nccl_comm_destroy.argtypes = [vp]
@@ -123,7 +124,7 @@ EXPORTS = ["haccsr_last_error", "haccsr_device_count", "haccsr_create", "haccsr_
            "haccsr_set_force_law", "haccsr_set_arithmetic", "haccsr_set_culling", "haccsr_upload", "haccsr_download", "haccsr_host_register",
            "haccsr_host_unregister", "haccsr_kick", "haccsr_kick_host", "haccsr_stream", "haccsr_partition_in_box",
            "haccsr_fill_mass", "haccsr_subcycle", "haccsr_map2_setup", "haccsr_map1_factor", "haccsr_particles_subcycle", "haccsr_cic", "haccsr_inverse_cic", "haccsr_refresh_message_bytes", "haccsr_refresh_begin",
-           "haccsr_refresh_pack", "haccsr_refresh_append", "haccsr_refresh", "haccsr_nccl_unique_id", "haccsr_nccl_comm_create",
+           "haccsr_refresh_pack", "haccsr_refresh_append", "haccsr_refresh", "haccsr_refresh_plan", "haccsr_nccl_unique_id", "haccsr_nccl_comm_create",
            "haccsr_nccl_comm_destroy", "haccsr_resident", "haccsr_get_tree", "haccsr_get_pseudo_particles",
            "haccsr_get_lists"]
 
@@ -383,3 +384,14 @@ def map2_setup(nglt, edge, gpscal, fscal, tau, step_fraction):
 
 def map1_factor(pp, tau, adot, alpha):
     return float(load_library().haccsr_map1_factor(pp, tau, adot, alpha))
+
+
+def refresh_plan(dims, rank):
+    """haccsr_refresh_plan: (direction of every message slot, destination rank of every slot) as haccsr_refresh orders them."""
+    lib = load_library()
+    d3 = (C.c_int32 * 3)(*[int(t) for t in dims])
+    order, dest = (C.c_int32 * 26)(), (C.c_int32 * 26)()
+    rc = lib.haccsr_refresh_plan(d3, int(rank), order, dest)
+    if rc != 0:
+        raise HaccSRError(lib.haccsr_last_error().decode())
+    return list(order), list(dest)

@@ -226,6 +226,12 @@ int haccsr_set_force_law(haccsr_ctx *c, int kind, const float *coeffs, int ncoef
   if (kind == HACCSR_LAW_SR_FIT && (ncoef != 8 || !coeffs)) { set_error("SR_FIT needs the 8 constants b c d e f g h l"); return 1; }
   if (kind == HACCSR_LAW_SR_INTERP && (ncoef < 2 || ncoef > 4096 || !coeffs)) { set_error("SR_INTERP needs a table of 2..4096 samples"); return 1; }
   if (!(rmax > 0.f)) { set_error("rmax must be positive"); return 1; }
+  // the reference's analytic fit is zero beyond FGrid::m_rmax whatever cutoff the tree is given (ForceLaw.cxx:32,70-80,187-192);
+  // the device applies the caller's cutoff only, so a larger one is refused rather than evaluated differently
+  if (kind == HACCSR_LAW_SR_FIT && rmax > 3.1163266f) {
+    set_error("SR_FIT: rmax %g exceeds the range of the grid-force fit (3.116326355, ForceLaw.cxx:32)", rmax);
+    return 1;
+  }
   HSR_CUDA(cudaSetDevice(c->device));
   memset(&c->law, 0, sizeof(c->law));
   c->law.kind = kind;

@@ -135,6 +135,7 @@ struct haccsr_ctx {
   haccsr::DevBuf<unsigned> tilecount, tilebase;     // per tile: counts and their exclusive scan (refresh.cu)
   haccsr::DevBuf<unsigned> scratch_u32;             // maxima for the fixed-point scales etc.
   haccsr::DevBuf<unsigned> scan_tmp;                // scan_exclusive on long inputs: per-block sums and their scan
+  int pass_tpb = 0, pass_occ = 0;                   // split pass: worker threads per block, resident blocks per SM (set on first use)
   haccsr::BuildState *h_state = nullptr;            // pinned
   haccsr::BuildState *d_state = nullptr;
   int64_t *h_counters = nullptr;                    // pinned, misc read-backs

@@ -128,6 +128,16 @@ using namespace haccsr;
 
 extern "C" {
 
+int haccsr_refresh_plan(const int32_t dims[3], int32_t rank, int32_t dir_of_slot[26], int32_t dest_of_slot[26]) {
+  if (!dims || !dir_of_slot || !dest_of_slot) { set_error("haccsr_refresh_plan: null argument"); return 1; }
+  Cart cart;
+  for (int k = 0; k < 3; ++k) { cart.dims[k] = dims[k]; if (dims[k] < 1) { set_error("haccsr_refresh_plan: bad decomposition"); return 1; } }
+  if (rank < 0 || rank >= cart.size()) { set_error("haccsr_refresh_plan: rank outside the decomposition"); return 1; }
+  const Plan p(cart, rank);
+  for (int q = 0; q < 26; ++q) { dir_of_slot[q] = p.order[q]; dest_of_slot[q] = p.dest[q]; }
+  return 0;
+}
+
 int haccsr_nccl_unique_id(void *id128) {
   if (!id128) { set_error("haccsr_nccl_unique_id: null buffer"); return 1; }
   NcclApi *api = nccl_api();

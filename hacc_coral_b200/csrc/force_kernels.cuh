@@ -239,7 +239,10 @@ __device__ __forceinline__ void interact2(const float4 s, SinkRegs2 &k, const Fo
 
 // Grid force g(r2) of the laws that only exist in scalar form (the per-pair cost is dominated by libm-grade
 // transcendentals or a table gather, so packing buys nothing).
-// LAW 2 = FGridEvalFit (reference ForceLaw.cxx:39-51,70-80) in the reference's order of operations, float:
+// LAW 2 = FGridEvalFit (reference ForceLaw.cxx:39-51,70-80), the reference's expression evaluated in float (the reference promotes
+// `1.0 + d r2`, `-1.0 d r2` and `2.0/3.0 b^3` to double and nvcc may contract here: agreement to FP32 rounding, gated against the
+// compiled reference's golden vectors in tests/test_gpu_parity.py::test_fit_and_interp_laws_match_reference; rmax beyond the
+// fit's own range is refused by haccsr_set_force_law):
 //   g = [tanh(br) - br/cosh^2(br) + c r^3 (1 + d r^2) exp(-d r^2) + e r^2 (f r^2 + g r^4 + l r^6) exp(-h r^2)] / r^3
 // LAW 3 = FGridEvalInterp (ForceLaw.cxx:145-172): linear interpolation in r2, zero outside (r2min, r2max).
 template <int LAW>

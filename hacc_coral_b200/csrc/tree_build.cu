@@ -1103,17 +1103,19 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
   cudaStream_t st = c->stream;
   // split pass geometry: 256 threads x 4 particles (1024-particle tiles, two blocks per SM); HACCSR_PASS_TPB=128 selects
   // 512-particle tiles, four blocks per SM (measured: the same 7.6 ms per build at 21.5 M particles)
-  static int ptpb = 0, occ_sp = 0;
-  if (!ptpb) {
+  // (per context: the shared-memory attribute and the occupancy belong to the context's device)
+  if (!c->pass_tpb) {
     const char *e = getenv("HACCSR_PASS_TPB");
     const int want = (e && atoi(e) == 128) ? 128 : 256;
     const void *fn = want == 256 ? (const void *)k_split_pass<256> : (const void *)k_split_pass<128>;
     const size_t dyn = (size_t)NST * want * IPT * 24;
+    int occ = 0;
     HSR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sp, fn, want + 32, dyn));
-    if (occ_sp < 1) { occ_sp = 0; set_error("k_split_pass does not fit on an SM"); return 2; }
-    ptpb = want;
+    HSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, want + 32, dyn));
+    if (occ < 1) { set_error("k_split_pass does not fit on an SM"); return 2; }
+    c->pass_tpb = want; c->pass_occ = occ;
   }
+  const int ptpb = c->pass_tpb, occ_sp = c->pass_occ;
   const int PT = ptpb * IPT;
   const int ntiles = (n + PT - 1) / PT;
   const int grid_sp = ntiles < c->sm_count * occ_sp ? (ntiles > 0 ? ntiles : 1) : c->sm_count * occ_sp;

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HACCSR_VERSION 2
+#define HACCSR_VERSION 3
 
 typedef struct haccsr_ctx haccsr_ctx;
 
@@ -274,6 +274,11 @@ typedef struct haccsr_refresh_stats {
 } haccsr_refresh_stats;
 int haccsr_refresh(haccsr_ctx *ctx, void *nccl_comm, const int32_t dims[3], int32_t rank, const float alive_lo[3],
                    const float alive_hi[3], float ol, haccsr_refresh_stats *stats);
+/* The message plan haccsr_refresh uses for `rank` (host arithmetic only, usable without a GPU): the 26 directions sorted by
+ * (destination rank, direction), so that the messages for one destination are contiguous in the send buffer and both sides
+ * derive the same layout from the counts alone.  dir_of_slot[s] = direction d = (sx+1)*9 + (sy+1)*3 + (sz+1) of message slot s,
+ * dest_of_slot[s] = the rank it goes to (periodic Cartesian neighbour, Partition.cxx:140-260). */
+int haccsr_refresh_plan(const int32_t dims[3], int32_t rank, int32_t dir_of_slot[26], int32_t dest_of_slot[26]);
 /* Communicator helpers for hosts that do not link NCCL themselves: rank 0 obtains an id, distributes its 128 bytes by its own
  * means (MPI_Bcast in HACC; torch.distributed in bench.py), every rank creates its communicator on its device. */
 #define HACCSR_NCCL_ID_BYTES 128

@@ -105,3 +105,18 @@ def test_refresh_over_gloo(dims):
     for rank, ok, ghosts, want_ghosts in res:
         assert ok, "rank %d: refreshed arrays differ from the oracle" % rank
         assert ghosts == want_ghosts and ghosts > 0
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 2, 4)])
+def test_c_plan_equals_python_plan(dims):
+    """The message plan of haccsr_refresh (C++, csrc/exchange.cu) is the plan of hacc_coral_b200/refresh.py that the gloo tests
+    above exercise: same slot order, same destinations, for every rank of the decomposition."""
+    from hacc_coral_b200 import capi
+    from hacc_coral_b200.refresh import Decomposition, RefreshPlan
+    size = dims[0] * dims[1] * dims[2]
+    for rank in range(size):
+        order, dest = capi.refresh_plan(dims, rank)
+        plan = RefreshPlan(Decomposition(dims, rank))
+        assert order == list(plan.order) and dest == list(plan.dest), rank
+    with pytest.raises(capi.HaccSRError):
+        capi.refresh_plan(dims, size)
