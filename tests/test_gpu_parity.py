@@ -750,3 +750,18 @@ def test_particles_outside_the_tree_box_and_large_masses(oracle):
         ia = np.array([ka[k] for k in ka if k[1] > 1]); ib = np.array([kb[k] for k in ka if k[1] > 1])
         pa, pb = o["tree"]["ppm"][ia].astype(np.float64), tree["ppm"][ib].astype(np.float64)
         assert np.all(np.abs(pa - pb) <= 2e-6 * np.abs(pa))
+
+
+def test_fit_law_refuses_a_cutoff_beyond_its_own_range():
+    """The reference's analytic grid-force fit is zero beyond FGrid::m_rmax = 3.116326355 whatever cutoff the tree gets
+    (ForceLaw.cxx:32,70-80,187-192); the device applies the caller's cutoff only, so a larger one is refused."""
+    from oracle import refbind
+    if not refbind.available():
+        pytest.skip("needs the compiled reference for the fit constants")
+    g = H.HaccSR(16)
+    try:
+        g.set_force_law(H.LAW_SR_FIT, refbind.fgrid_constants(), RSM, H.RMAX)          # the fit's own range: fine
+        with pytest.raises(H.HaccSRError):
+            g.set_force_law(H.LAW_SR_FIT, refbind.fgrid_constants(), RSM, 3.5)
+    finally:
+        g.close()
