@@ -19,8 +19,9 @@
 // of summation order: the build is deterministic, and the float centroid equals the reference's
 // (double-accumulated) one except where the reference's own rounding error straddles a float boundary.
 // Children are numbered breadth-first (parent index < child index, as the reference guarantees at :808-809).
-// Left blocks keep input order like the reference; right blocks are written back to front (the reference's
-// right-block order is an artefact of its swap loop and only affects FP32 summation order).
+// Left blocks keep input order like the reference; right blocks are kept in input order too (written back to front, un-mirrored
+// through a per-node direction: k_split_pass) where the reference's swap loop scrambles them -- that order only affects the FP32
+// summation order inside a leaf.  The level where nothing splits any more is finalised by k_gather.
 #include "common.cuh"
 
 #include <float.h>
@@ -33,7 +34,7 @@ namespace haccsr {
 
 static constexpr int TILE = 1024;      // particles per tile / thread block
 static constexpr int TPB = 256;        // threads per block in tile kernels
-static constexpr int IPT = TILE / TPB; // items per thread (k_cm_tile: consecutive; flag/scatter passes: striped i = base + j*TPB + t)
+static constexpr int IPT = TILE / TPB; // items per thread in the split pass (striped: particle = tile base + j * threads + t)
 static constexpr int SMAX = 32;        // node runs per tile accumulated in shared memory
 
 // ---- helpers ---------------------------------------------------------------------------------
