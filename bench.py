@@ -677,10 +677,12 @@ def main():
                 "kind": "reference",
                 "sample": "SAMPLED: %d^3-cell cut-out (%d particles, %d pairs) of rank 0's snapshot, full RCBMonopoleForceTree ctor%s, %.1f s" % (
                     info["side"], info["particles"], info["pairs"], info["note"], info["seconds"])}
-    print(json.dumps(line))
-    sys.stdout.flush()
+    # the JSON line is the last thing on stdout: NCCL (NCCL_DEBUG) may still write while the process group is torn down
     if dist is not None:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    print(json.dumps(line))
+    sys.stdout.flush()
     return 0
 
 
