@@ -197,19 +197,25 @@ int haccsr_refresh(haccsr_ctx *c, void *nccl_comm, const int32_t dims[3], int32_
   // 1. drop the ghosts, classify the alive particles against the 26 slabs, message sizes (refresh.cu)
   int64_t counts[27], n_alive = 0;
   HSR_TRY(haccsr_refresh_begin(c, alive_lo, alive_hi, ol, mine.slot_of_dir, counts, &n_alive));
-  // 2. every rank's 26 counts to every rank (tiny all-gather on the device), then one read-back
-  std::vector<long long> table((size_t)nranks * 26);
-  HSR_TRY(c->xchg_table.ensure((size_t)nranks * 26 + 26 + 3 * 26 * (size_t)nranks + 64));
-  long long *d_table = c->xchg_table.p;                  // [nranks][26]
-  long long *d_mine = d_table + (size_t)nranks * 26;     // [26]
+  // 2. every rank's row -- its 26 counts, its alive count and its capacity -- to every rank (tiny all-gather on the device),
+  //    then one read-back.  With the last two every rank sees which ranks cannot hold their ghosts, so that all of them
+  //    leave the call with the same status instead of some waiting in the exchange for a peer that has already returned.
+  constexpr int ROW = 28;
+  std::vector<long long> table((size_t)nranks * ROW);
+  HSR_TRY(c->xchg_table.ensure((size_t)nranks * ROW + 32 + 3 * 26 * (size_t)nranks + 64));
+  long long *d_table = c->xchg_table.p;                  // [nranks][ROW]
+  long long *d_mine = d_table + (size_t)nranks * ROW;    // [ROW]
   AppendEntry *d_app = reinterpret_cast<AppendEntry *>(d_mine + 32);
+  long long row[ROW];
+  for (int q = 0; q < 26; ++q) row[q] = counts[q];
+  row[26] = n_alive; row[27] = c->cap;
   if (nranks > 1) {
-    HSR_CUDA(cudaMemcpyAsync(d_mine, counts, 26 * sizeof(long long), cudaMemcpyHostToDevice, s));
-    HSR_NCCL(api, api->AllGather(d_mine, d_table, 26, ncclInt64, comm, s));
+    HSR_CUDA(cudaMemcpyAsync(d_mine, row, ROW * sizeof(long long), cudaMemcpyHostToDevice, s));
+    HSR_NCCL(api, api->AllGather(d_mine, d_table, ROW, ncclInt64, comm, s));
     HSR_CUDA(cudaMemcpyAsync(table.data(), d_table, table.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
     HSR_CUDA(cudaStreamSynchronize(s));
   } else {
-    for (int q = 0; q < 26; ++q) table[q] = counts[q];
+    for (int q = 0; q < ROW; ++q) table[q] = row[q];
   }
   // 3. layouts: my messages sorted by destination; what each rank sends to me, in the order it sits in that rank's chunk
   int64_t off[27];
@@ -224,13 +230,15 @@ int haccsr_refresh(haccsr_ctx *c, void *nccl_comm, const int32_t dims[3], int32_
   const long long total_send = pos;
   for (int r = 0; r < nranks; ++r) send_off[r + 1] = send_off[r] + send_bytes[r];
   std::vector<AppendEntry> app;
+  std::vector<long long> incoming(nranks, 0);     // ghosts every rank is about to receive
   long long rpos = 0, at = n_alive, ghosts = 0;
   for (int r = 0; r < nranks; ++r) {
     const Plan theirs(cart, r);
     recv_off[r] = rpos;
     for (int q = 0; q < 26; ++q) {
+      const long long n = table[(size_t)r * ROW + q];
+      incoming[theirs.dest[q]] += n;
       if (theirs.dest[q] != rank) continue;
-      const long long n = table[(size_t)r * 26 + q];
       if (n > 0) { app.push_back({rpos, n, at}); at += n; ghosts += n; }
       rpos += haccsr_refresh_message_bytes(n);
     }
@@ -238,9 +246,12 @@ int haccsr_refresh(haccsr_ctx *c, void *nccl_comm, const int32_t dims[3], int32_
   }
   recv_off[nranks] = rpos;
   const long long total_recv = rpos;
-  if (at > c->cap) {
-    set_error("haccsr_refresh: %lld alive + %lld ghosts exceed the context capacity %lld", (long long)n_alive, ghosts, (long long)c->cap);
-    return 1;
+  for (int r = 0; r < nranks; ++r) {
+    const long long alive_r = table[(size_t)r * ROW + 26], cap_r = table[(size_t)r * ROW + 27];
+    if (alive_r + incoming[r] > cap_r) {      // the same verdict on every rank; the contexts keep their alive particles
+      set_error("haccsr_refresh: %lld alive + %lld ghosts exceed the context capacity %lld on rank %d", alive_r, incoming[r], cap_r, r);
+      return 1;
+    }
   }
   HSR_TRY(c->xchg_send.ensure((size_t)total_send + 16));
   HSR_TRY(c->xchg_recv.ensure((size_t)total_recv + 16));

@@ -264,7 +264,9 @@ int64_t haccsr_resident(haccsr_ctx *ctx);
  * every neighbour is the rank itself).  Collective: every rank of the communicator must call it.  On return the context
  * holds its alive particles (stable order) followed by the received ghosts in (source rank, direction) order --
  * deterministic, and bit-identical to extracting each rank's overloaded sub-volume from the global particle set.
- * NCCL is loaded at run time (libnccl.so.2); status 3 if it cannot be. */
+ * NCCL is loaded at run time (libnccl.so.2); status 3 if it cannot be.  If the ghosts of ANY rank would not fit in that rank's
+ * context (alive + incoming > capacity), every rank returns 1 with the same message before anything is exchanged (alive counts
+ * and capacities travel with the message sizes), and every context is left holding its alive particles only. */
 typedef struct haccsr_refresh_stats {
   int64_t alive, ghosts, sent;             /* particles kept, received, sent (a particle goes to up to 7 neighbours)       */
   int64_t bytes_sent, bytes_received;      /* packed message bytes, self messages included                                 */

@@ -128,6 +128,25 @@ def test_c_abi_refresh_rejects_bad_arguments():
     g.close()
 
 
+def test_c_abi_refresh_capacity_is_checked_before_the_exchange():
+    """A context too small for its ghosts: haccsr_refresh returns an error that names the rank before anything is exchanged
+    (every rank reaches the same verdict from the gathered table), and the context keeps its alive particles."""
+    dims = (1, 1, 1)
+    pos, vel = U.global_particles(dims, EXT, 30000, seed=13)
+    dec = Decomposition(dims, 0)
+    p = U.rank_particles(pos, vel, dims, dec.pos, EXT, OL, seed=0)
+    m = (p["x"] >= ALO[0]) & (p["x"] < AHI[0]) & (p["y"] >= ALO[1]) & (p["y"] < AHI[1]) & (p["z"] >= ALO[2]) & (p["z"] < AHI[2])
+    q = {k: v[m] for k, v in p.items()}
+    alive = int(m.sum())
+    assert alive == 30000
+    g = H.HaccSR(alive + 10)                   # the ghosts (thousands) do not fit
+    g.upload(q)
+    with pytest.raises(H.HaccSRError, match="on rank 0"):
+        g.refresh(None, dims, 0, ALO, AHI, OL)
+    assert g.resident() == alive
+    g.close()
+
+
 def test_kick_between_begin_and_pack_is_refused():
     """The candidate list of haccsr_refresh_begin indexes the particles as they lay at that moment (it lives in its own
     buffer, not in the build's scratch); a kick in between permutes them, and haccsr_refresh_pack refuses to pack stale
