@@ -1103,7 +1103,7 @@ int build_tree(haccsr_ctx *c, int64_t n64, const float lo[3], const float hi[3],
   const int ppn = (int)(ppn64 > INT_MAX ? INT_MAX : ppn64);
   cudaStream_t st = c->stream;
   // split pass geometry: 256 threads x 4 particles (1024-particle tiles, two blocks per SM); HACCSR_PASS_TPB=128 selects
-  // 512-particle tiles, four blocks per SM (measured: the same 7.6 ms per build at 21.5 M particles)
+  // 512-particle tiles, three blocks per SM (measured: 6.6 against 5.9 ms per build at 21.5 M particles)
   // (per context: the shared-memory attribute and the occupancy belong to the context's device)
   if (!c->pass_tpb) {
     const char *e = getenv("HACCSR_PASS_TPB");
